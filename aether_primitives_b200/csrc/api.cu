@@ -1,0 +1,1314 @@
+// api.cu — host side of the C ABI declared in include/aether_b200.h: device contexts, buffer
+// handles with the lazy VecOps op tape, plans (FFT, FIR, modulation, AWGN, chains) and the
+// status-code error model.  No CPU compute path exists here: every data operation launches a
+// kernel from elementwise.cu / fft.cu / fir.cu / chain.cu on the context's stream.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+
+using namespace ae;
+
+// =================================================================================================
+// context / errors
+// =================================================================================================
+namespace {
+
+struct Alloc {
+  void* p = nullptr;
+  size_t bytes = 0;
+  bool owned = true;
+  int refs = 1;
+};
+
+struct Ctx {
+  int dev = 0;
+  cudaStream_t own = nullptr, stream = nullptr;
+  int sm_count = 148;
+  int* d_err = nullptr;
+  std::vector<ae_vec*> pending;               // vecs with a non-empty tape
+  std::map<size_t, float2*> tw_cache;         // twiddle tables by length
+  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+};
+
+constexpr int kMaxDev = 64;
+Ctx* g_ctx[kMaxDev] = {nullptr};
+std::mutex g_mu;
+thread_local int t_dev = -1;
+thread_local std::string t_err = "";
+std::atomic<uint64_t> g_launches{0};
+
+ae_status fail(ae_status st, const std::string& msg) {
+  t_err = msg;
+  return st;
+}
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      if (e__ == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(AE_EOOM, std::string("out of device memory: ") + #call); } \
+      return fail(AE_ECUDA, std::string(cudaGetErrorString(e__)) + " in " + #call);           \
+    }                                                                                         \
+  } while (0)
+#define CKL(n)                                                                                \
+  do {                                                                                        \
+    g_launches += (n);                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess) return fail(AE_ECUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e__)); \
+  } while (0)
+#define TRY(expr)                        \
+  do {                                   \
+    ae_status s__ = (expr);              \
+    if (s__ != AE_OK) return s__;        \
+  } while (0)
+
+ae_status get_ctx(Ctx** out) {
+  if (t_dev < 0) {
+    ae_status s = ae_init(0);
+    if (s != AE_OK) return s;
+  }
+  Ctx* c = g_ctx[t_dev];
+  cudaError_t e = cudaSetDevice(c->dev);
+  if (e != cudaSuccess) return fail(AE_ECUDA, cudaGetErrorString(e));
+  *out = c;
+  return AE_OK;
+}
+
+ae_status dev_alloc(Ctx* c, size_t bytes, void** p) {
+  if (bytes == 0) bytes = 256;
+  bytes = (bytes + 255) & ~(size_t)255;
+  CK(cudaMallocAsync(p, bytes, c->stream));
+  return AE_OK;
+}
+void dev_free(Ctx* c, void* p) {
+  if (p) cudaFreeAsync(p, c->stream);
+}
+
+Alloc* alloc_new(Ctx* c, size_t bytes, ae_status* st) {
+  void* p = nullptr;
+  *st = dev_alloc(c, bytes, &p);
+  if (*st != AE_OK) return nullptr;
+  Alloc* a = new Alloc;
+  a->p = p; a->bytes = bytes; a->owned = true; a->refs = 1;
+  return a;
+}
+void alloc_unref(Ctx* c, Alloc* a) {
+  if (!a) return;
+  if (--a->refs == 0) {
+    if (a->owned) dev_free(c, a->p);
+    delete a;
+  }
+}
+
+ae_status get_twiddles(Ctx* c, size_t n, float2** out) {
+  auto it = c->tw_cache.find(n);
+  if (it != c->tw_cache.end()) { *out = it->second; return AE_OK; }
+  std::vector<float2> h(n);
+  for (size_t k = 0; k < n; ++k) {
+    const double a = -2.0 * M_PI * (double)k / (double)n;   // f64, rounded to f32 (rustfft's accuracy class)
+    h[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  void* p = nullptr;
+  TRY(dev_alloc(c, n * sizeof(float2), &p));
+  CK(cudaMemcpyAsync(p, h.data(), n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->tw_cache[n] = (float2*)p;
+  *out = (float2*)p;
+  return AE_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// handle types
+// =================================================================================================
+struct TapeRec {
+  int op;
+  float s;
+  Alloc* oa;     // operand allocation (ref held) or null
+  size_t ooff;   // operand offset in elements
+};
+struct ae_vec {
+  Ctx* c;
+  Alloc* a;
+  size_t off, len, cap;
+  std::vector<TapeRec> tape;
+  bool plan_owned;  // scratch view handed out by a plan: ae_vec_free is a no-op
+};
+struct ae_bits {
+  Ctx* c;
+  Alloc* a;
+  size_t off, len, cap;
+};
+
+namespace {
+
+inline float2* vptr(const ae_vec* v) { return reinterpret_cast<float2*>(v->a->p) + v->off; }
+inline uint8_t* bptr(const ae_bits* b) { return reinterpret_cast<uint8_t*>(b->a->p) + b->off; }
+
+void drop_pending(ae_vec* v) {
+  auto& p = v->c->pending;
+  p.erase(std::remove(p.begin(), p.end(), v), p.end());
+}
+
+ae_status flush_vec(ae_vec* v) {
+  if (v->tape.empty()) return AE_OK;
+  TapeParams tp;
+  std::memset(&tp, 0, sizeof(tp));
+  bool has_mirror = false;
+  int n = 0;
+  for (const TapeRec& r : v->tape) {
+    tp.e[n].op = r.op;
+    tp.e[n].s = r.s;
+    tp.e[n].operand = r.oa ? reinterpret_cast<const float2*>(r.oa->p) + r.ooff : nullptr;
+    has_mirror |= (r.op == OP_MIRROR);
+    ++n;
+  }
+  tp.n_ops = n;
+  tp.load_self = !(v->tape[0].op == OP_ZERO || v->tape[0].op == OP_CLONE);
+  launch_vecops(vptr(v), v->len, tp, has_mirror, v->c->sm_count, v->c->stream);
+  for (TapeRec& r : v->tape) alloc_unref(v->c, r.oa);
+  v->tape.clear();
+  drop_pending(v);
+  if (v->len) CKL(1);
+  return AE_OK;
+}
+
+bool tape_reads(const ae_vec* p, const Alloc* a) {
+  for (const TapeRec& r : p->tape)
+    if (r.oa == a) return true;
+  return false;
+}
+// make the memory behind `v` current (its own tape and any alias of the same allocation)
+ae_status before_read(ae_vec* v) {
+  std::vector<ae_vec*> snap = v->c->pending;
+  for (ae_vec* p : snap)
+    if (p->a == v->a) TRY(flush_vec(p));
+  return AE_OK;
+}
+// additionally run every tape that still wants to read the old contents of `v`
+ae_status before_write(ae_vec* v) {
+  std::vector<ae_vec*> snap = v->c->pending;
+  for (ae_vec* p : snap)
+    if (p->a == v->a || tape_reads(p, v->a)) TRY(flush_vec(p));
+  return AE_OK;
+}
+
+ae_status record(ae_vec* v, int op, ae_vec* other, float s) {
+  if (!v) return fail(AE_EARG, "null vector handle");
+  const bool binary = (op == OP_MUL || op == OP_DIV || op == OP_ADD || op == OP_SUB || op == OP_CLONE);
+  if (binary) {
+    if (!other) return fail(AE_EARG, "null operand handle");
+    if (other->len != v->len) return fail(AE_ELEN, "Vectors must have same length");  // src/vecops.rs:100-104
+    if (other->c != v->c) return fail(AE_EARG, "operand lives on another device");
+  }
+  std::vector<ae_vec*> snap = v->c->pending;
+  for (ae_vec* p : snap) {
+    if (p == v) continue;
+    if (p->a == v->a || tape_reads(p, v->a) || (binary && p->a == other->a)) TRY(flush_vec(p));
+  }
+  if (binary && other->a == v->a) TRY(flush_vec(v));  // operand aliases self: snapshot current values
+  if ((int)v->tape.size() >= kMaxTape) TRY(flush_vec(v));
+  if (op == OP_ZERO || op == OP_CLONE) {  // everything recorded before is dead
+    for (TapeRec& r : v->tape) alloc_unref(v->c, r.oa);
+    v->tape.clear();
+  }
+  TapeRec r;
+  r.op = op; r.s = s; r.oa = nullptr; r.ooff = 0;
+  if (binary) { r.oa = other->a; r.ooff = other->off; other->a->refs++; }
+  if (v->tape.empty()) v->c->pending.push_back(v);
+  v->tape.push_back(r);
+  return AE_OK;
+}
+
+ae_status vec_reserve(ae_vec* v, size_t cap) {
+  if (cap <= v->cap) return AE_OK;
+  if (!v->a->owned || v->plan_owned) return fail(AE_EARG, "cannot grow a borrowed or plan-owned vector");
+  TRY(before_write(v));
+  size_t ncap = std::max(cap, v->cap * 2);
+  ae_status st;
+  Alloc* na = alloc_new(v->c, ncap * sizeof(float2), &st);
+  if (!na) return st;
+  if (v->len) CK(cudaMemcpyAsync(na->p, vptr(v), v->len * sizeof(float2), cudaMemcpyDeviceToDevice, v->c->stream));
+  alloc_unref(v->c, v->a);
+  v->a = na; v->off = 0; v->cap = ncap;
+  return AE_OK;
+}
+ae_status bits_reserve(ae_bits* b, size_t cap) {
+  if (cap <= b->cap) return AE_OK;
+  if (!b->a->owned) return fail(AE_EARG, "cannot grow a borrowed bit vector");
+  size_t ncap = std::max(cap, b->cap * 2);
+  ae_status st;
+  Alloc* na = alloc_new(b->c, ncap, &st);
+  if (!na) return st;
+  if (b->len) CK(cudaMemcpyAsync(na->p, bptr(b), b->len, cudaMemcpyDeviceToDevice, b->c->stream));
+  alloc_unref(b->c, b->a);
+  b->a = na; b->off = 0; b->cap = ncap;
+  return AE_OK;
+}
+
+float scale_factor(int kind, size_t n, float x) {  // src/fft.rs:22-37
+  switch (kind) {
+    case AE_SCALE_SN: return 1.0f / sqrtf((float)n);
+    case AE_SCALE_N: return 1.0f / (float)n;
+    case AE_SCALE_X: return x;
+    default: return 1.0f;
+  }
+}
+
+}  // namespace
+
+// =================================================================================================
+// runtime
+// =================================================================================================
+extern "C" {
+
+const char* ae_version(void) { return "aether_b200 0.1.0 (sm_100a)"; }
+
+ae_status ae_device_count(int* n) {
+  if (!n) return fail(AE_EARG, "null");
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) { *n = 0; cudaGetLastError(); return fail(AE_ECUDA, cudaGetErrorString(e)); }
+  return AE_OK;
+}
+
+ae_status ae_init(int device) {
+  if (device < 0 || device >= kMaxDev) return fail(AE_EARG, "bad device index");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(AE_ECUDA, "no CUDA device available: aether_b200 has no CPU fallback");
+  }
+  if (device >= n) return fail(AE_EARG, "device index out of range");
+  CK(cudaSetDevice(device));
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_ctx[device]) {
+    Ctx* c = new Ctx;
+    c->dev = device;
+    CK(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
+    c->stream = c->own;
+    for (int i = 0; i < 3; ++i) CK(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) {
+      delete c;
+      return fail(AE_ECUDA, "aether_b200 kernels are built for sm_100a (B200) only; found compute capability " +
+                                std::to_string(prop.major) + "." + std::to_string(prop.minor));
+    }
+    CK(cudaMalloc((void**)&c->d_err, sizeof(int)));
+    CK(cudaMemset(c->d_err, 0, sizeof(int)));
+    // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    g_ctx[device] = c;
+  }
+  t_dev = device;
+  return AE_OK;
+}
+
+ae_status ae_set_stream(void* cuda_stream) {
+  Ctx* c;
+  TRY(get_ctx(&c));
+  cudaStream_t ns = cuda_stream ? (cudaStream_t)cuda_stream : c->own;
+  if (ns != c->stream) {
+    // order the new stream after everything already issued on the old one
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, c->stream));
+    CK(cudaStreamWaitEvent(ns, ev, 0));
+    CK(cudaEventDestroy(ev));
+    c->stream = ns;
+  }
+  return AE_OK;
+}
+void* ae_get_stream(void) {
+  Ctx* c;
+  if (get_ctx(&c) != AE_OK) return nullptr;
+  return (void*)c->stream;
+}
+
+ae_status ae_sync(void) {
+  Ctx* c;
+  TRY(get_ctx(&c));
+  int flag = 0;
+  CK(cudaMemcpyAsync(&flag, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (flag) {
+    CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+    if (flag & DEVERR_MOD_INDEX) return fail(AE_EIDX, "index out of bounds: the len is 2 or 4 but a bit pattern selected a larger table index");
+    return fail(AE_ECUDA, "device-side error flag set");
+  }
+  return AE_OK;
+}
+const char* ae_last_error_string(void) { return t_err.c_str(); }
+ae_status ae_sm_count(int* n) {
+  Ctx* c;
+  TRY(get_ctx(&c));
+  *n = c->sm_count;
+  return AE_OK;
+}
+uint64_t ae_launch_count(void) { return g_launches.load(); }
+
+ae_status ae_host_alloc(size_t bytes, void** p) {
+  Ctx* c;
+  TRY(get_ctx(&c));
+  CK(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault));
+  return AE_OK;
+}
+ae_status ae_host_free(void* p) {
+  if (p) CK(cudaFreeHost(p));
+  return AE_OK;
+}
+
+// =================================================================================================
+// ae_vec
+// =================================================================================================
+ae_status ae_vec_alloc(size_t len, size_t capacity, ae_vec** out) {
+  if (!out) return fail(AE_EARG, "null out");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  if (capacity < len) capacity = len;
+  ae_status st;
+  Alloc* a = alloc_new(c, capacity * sizeof(float2), &st);
+  if (!a) return st;
+  if (len) CK(cudaMemsetAsync(a->p, 0, len * sizeof(float2), c->stream));
+  ae_vec* v = new ae_vec;
+  v->c = c; v->a = a; v->off = 0; v->len = len; v->cap = capacity; v->plan_owned = false;
+  *out = v;
+  return AE_OK;
+}
+ae_status ae_vec_wrap(void* device_ptr, size_t len, ae_vec** out) {
+  if (!out || (!device_ptr && len)) return fail(AE_EARG, "null");
+  if (((uintptr_t)device_ptr % 8) != 0) return fail(AE_EARG, "cf32 buffers must be 8-byte aligned");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  Alloc* a = new Alloc;
+  a->p = device_ptr; a->bytes = len * sizeof(float2); a->owned = false; a->refs = 1;
+  ae_vec* v = new ae_vec;
+  v->c = c; v->a = a; v->off = 0; v->len = len; v->cap = len; v->plan_owned = false;
+  *out = v;
+  return AE_OK;
+}
+ae_status ae_vec_view(ae_vec* parent, size_t offset, size_t len, ae_vec** out) {
+  if (!parent || !out) return fail(AE_EARG, "null");
+  if (offset > parent->len || len > parent->len - offset) return fail(AE_EIDX, "range end index out of range for slice");
+  ae_vec* v = new ae_vec;
+  v->c = parent->c; v->a = parent->a; parent->a->refs++;
+  v->off = parent->off + offset; v->len = len; v->cap = len; v->plan_owned = false;
+  *out = v;
+  return AE_OK;
+}
+ae_status ae_vec_free(ae_vec* v) {
+  if (!v || v->plan_owned) return AE_OK;
+  cudaSetDevice(v->c->dev);
+  ae_status st = AE_OK;
+  if (v->a->refs > 1) st = flush_vec(v);  // someone else can still observe the memory
+  else {
+    for (TapeRec& r : v->tape) alloc_unref(v->c, r.oa);
+    v->tape.clear();
+    drop_pending(v);
+  }
+  // tapes that read this allocation keep it alive through their own reference
+  alloc_unref(v->c, v->a);
+  delete v;
+  return st;
+}
+size_t ae_vec_len(const ae_vec* v) { return v ? v->len : 0; }
+size_t ae_vec_capacity(const ae_vec* v) { return v ? v->cap : 0; }
+ae_status ae_vec_set_len(ae_vec* v, size_t len) {
+  if (!v) return fail(AE_EARG, "null");
+  if (len > v->cap) return fail(AE_EARG, "len exceeds capacity");
+  TRY(flush_vec(v));
+  v->len = len;
+  return AE_OK;
+}
+ae_status ae_vec_reserve(ae_vec* v, size_t capacity) {
+  if (!v) return fail(AE_EARG, "null");
+  cudaSetDevice(v->c->dev);
+  return vec_reserve(v, capacity);
+}
+ae_status ae_vec_device_ptr(ae_vec* v, void** ptr) {
+  if (!v || !ptr) return fail(AE_EARG, "null");
+  cudaSetDevice(v->c->dev);
+  TRY(before_write(v));
+  *ptr = vptr(v);
+  return AE_OK;
+}
+ae_status ae_vec_upload(ae_vec* v, const ae_cf32* host, size_t n) {
+  if (!v || (!host && n)) return fail(AE_EARG, "null");
+  if (n != v->len) return fail(AE_ELEN, "Vectors must have same length");
+  cudaSetDevice(v->c->dev);
+  TRY(before_write(v));
+  if (n) {
+    CK(cudaMemcpyAsync(vptr(v), host, n * sizeof(float2), cudaMemcpyHostToDevice, v->c->stream));
+    CK(cudaStreamSynchronize(v->c->stream));
+  }
+  return AE_OK;
+}
+ae_status ae_vec_download(ae_vec* v, ae_cf32* host, size_t n) {
+  if (!v || (!host && n)) return fail(AE_EARG, "null");
+  if (n != v->len) return fail(AE_ELEN, "Vectors must have same length");
+  cudaSetDevice(v->c->dev);
+  TRY(before_read(v));
+  if (n) CK(cudaMemcpyAsync(host, vptr(v), n * sizeof(float2), cudaMemcpyDeviceToHost, v->c->stream));
+  return ae_sync();
+}
+
+ae_status ae_vec_scale(ae_vec* v, float s) { return record(v, OP_SCALE, nullptr, s); }
+ae_status ae_vec_mul(ae_vec* v, ae_vec* o) { return record(v, OP_MUL, o, 0.f); }
+ae_status ae_vec_div(ae_vec* v, ae_vec* o) { return record(v, OP_DIV, o, 0.f); }
+ae_status ae_vec_conj(ae_vec* v) { return record(v, OP_CONJ, nullptr, 0.f); }
+ae_status ae_vec_add(ae_vec* v, ae_vec* o) { return record(v, OP_ADD, o, 0.f); }
+ae_status ae_vec_sub(ae_vec* v, ae_vec* o) { return record(v, OP_SUB, o, 0.f); }
+ae_status ae_vec_mirror(ae_vec* v) { return record(v, OP_MIRROR, nullptr, 0.f); }
+ae_status ae_vec_clone(ae_vec* v, ae_vec* o) { return record(v, OP_CLONE, o, 0.f); }
+ae_status ae_vec_zero(ae_vec* v) { return record(v, OP_ZERO, nullptr, 0.f); }
+ae_status ae_vec_flush(ae_vec* v) {
+  if (!v) return fail(AE_EARG, "null");
+  cudaSetDevice(v->c->dev);
+  return flush_vec(v);
+}
+size_t ae_vec_pending_ops(const ae_vec* v) { return v ? v->tape.size() : 0; }
+
+ae_status ae_vec_mutate(ae_vec* v, void (*f)(ae_cf32*, void*), void* user) {
+  if (!v || !f) return fail(AE_EARG, "null");
+  // arbitrary host closure in element order (src/vecops.rs:179-182): documented slow path
+  std::vector<ae_cf32> h(v->len);
+  TRY(ae_vec_download(v, h.data(), v->len));
+  for (size_t i = 0; i < v->len; ++i) f(&h[i], user);
+  return ae_vec_upload(v, h.data(), v->len);
+}
+
+ae_status ae_scale_factor(int kind, size_t n, float x, float* s) {
+  if (!s || kind < 0 || kind > 3) return fail(AE_EARG, "bad scale kind");
+  *s = scale_factor(kind, n, x);
+  return AE_OK;
+}
+ae_status ae_vec_scale_kind(ae_vec* v, int kind, float x) {
+  if (!v || kind < 0 || kind > 3) return fail(AE_EARG, "bad scale kind");
+  if (kind == AE_SCALE_NONE) return AE_OK;  // src/fft.rs:24
+  return record(v, OP_SCALE, nullptr, scale_factor(kind, v->len, x));
+}
+
+// =================================================================================================
+// ae_bits
+// =================================================================================================
+ae_status ae_bits_alloc(size_t len, size_t capacity, ae_bits** out) {
+  if (!out) return fail(AE_EARG, "null out");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  if (capacity < len) capacity = len;
+  ae_status st;
+  Alloc* a = alloc_new(c, capacity, &st);
+  if (!a) return st;
+  if (len) CK(cudaMemsetAsync(a->p, 0, len, c->stream));
+  ae_bits* b = new ae_bits;
+  b->c = c; b->a = a; b->off = 0; b->len = len; b->cap = capacity;
+  *out = b;
+  return AE_OK;
+}
+ae_status ae_bits_wrap(void* device_ptr, size_t len, ae_bits** out) {
+  if (!out || (!device_ptr && len)) return fail(AE_EARG, "null");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  Alloc* a = new Alloc;
+  a->p = device_ptr; a->bytes = len; a->owned = false; a->refs = 1;
+  ae_bits* b = new ae_bits;
+  b->c = c; b->a = a; b->off = 0; b->len = len; b->cap = len;
+  *out = b;
+  return AE_OK;
+}
+ae_status ae_bits_free(ae_bits* b) {
+  if (!b) return AE_OK;
+  cudaSetDevice(b->c->dev);
+  alloc_unref(b->c, b->a);
+  delete b;
+  return AE_OK;
+}
+size_t ae_bits_len(const ae_bits* b) { return b ? b->len : 0; }
+size_t ae_bits_capacity(const ae_bits* b) { return b ? b->cap : 0; }
+ae_status ae_bits_set_len(ae_bits* b, size_t len) {
+  if (!b) return fail(AE_EARG, "null");
+  if (len > b->cap) return fail(AE_EARG, "len exceeds capacity");
+  b->len = len;
+  return AE_OK;
+}
+ae_status ae_bits_device_ptr(ae_bits* b, void** ptr) {
+  if (!b || !ptr) return fail(AE_EARG, "null");
+  *ptr = bptr(b);
+  return AE_OK;
+}
+ae_status ae_bits_upload(ae_bits* b, const uint8_t* host, size_t n) {
+  if (!b || (!host && n)) return fail(AE_EARG, "null");
+  if (n != b->len) return fail(AE_ELEN, "Vectors must have same length");
+  cudaSetDevice(b->c->dev);
+  if (n) {
+    CK(cudaMemcpyAsync(bptr(b), host, n, cudaMemcpyHostToDevice, b->c->stream));
+    CK(cudaStreamSynchronize(b->c->stream));
+  }
+  return AE_OK;
+}
+ae_status ae_bits_download(ae_bits* b, uint8_t* host, size_t n) {
+  if (!b || (!host && n)) return fail(AE_EARG, "null");
+  if (n != b->len) return fail(AE_ELEN, "Vectors must have same length");
+  cudaSetDevice(b->c->dev);
+  if (n) CK(cudaMemcpyAsync(host, bptr(b), n, cudaMemcpyDeviceToHost, b->c->stream));
+  return ae_sync();
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// FFT
+// =================================================================================================
+struct ae_fft {
+  Ctx* c;
+  size_t len;
+  int compat;
+  float2* tw;
+  bool pow2;
+  std::vector<uint32_t> radices;
+  float2* scratch;
+  size_t scratch_elems;
+  Alloc* tmp;       // tfwd/tbwd result buffer
+  size_t tmp_elems;
+  ae_vec tmpview;
+};
+
+namespace {
+
+ae_status fft_run(ae_fft* f, int dir, const float2* in, float2* out, int scale_kind, float x, size_t howmany) {
+  Ctx* c = f->c;
+  // reference compat: Cfft "fwd" = rustfft inverse = exp(+) (src/fft.rs:148)
+  const bool fwd_is_inverse = (f->compat == AE_COMPAT_REFERENCE);
+  const bool inverse = (dir == AE_FFT_FWD) ? fwd_is_inverse : !fwd_is_inverse;
+  const bool do_scale = scale_kind != AE_SCALE_NONE;
+  const float s = scale_factor(scale_kind, f->len, x);  // N = the slice length passed (one frame)
+  if (howmany == 0) return AE_OK;
+  if (f->pow2) {
+    launch_fft_pow2(in, out, f->len, howmany, f->tw, inverse, do_scale, s, c->stream);
+    CKL(1);
+  } else {
+    const size_t need = 2 * f->len * howmany;
+    if (f->scratch_elems < need) {
+      dev_free(c, f->scratch);
+      f->scratch = nullptr; f->scratch_elems = 0;
+      void* p;
+      TRY(dev_alloc(c, need * sizeof(float2), &p));
+      f->scratch = (float2*)p; f->scratch_elems = need;
+    }
+    launch_fft_generic(in, out, f->scratch, f->len, howmany, f->tw, f->radices.data(), (int)f->radices.size(), inverse,
+                       do_scale, s, c->stream);
+    CKL(std::max<size_t>(1, f->radices.size()) * ((howmany + 32767) / 32768));
+  }
+  return AE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+ae_status ae_fft_create(size_t len, ae_fft** out) {
+  if (!out) return fail(AE_EARG, "null out");
+  if (len == 0) return fail(AE_EARG, "FFT length must be >= 1");
+  if (len > (1ull << 31)) return fail(AE_EARG, "FFT length too large");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  ae_fft* f = new ae_fft;
+  f->c = c; f->len = len; f->compat = AE_COMPAT_REFERENCE;
+  f->pow2 = fft_pow2_supported(len);
+  f->scratch = nullptr; f->scratch_elems = 0; f->tmp = nullptr; f->tmp_elems = 0;
+  ae_status st = get_twiddles(c, len, &f->tw);
+  if (st != AE_OK) { delete f; return st; }
+  if (!f->pow2) {
+    size_t m = len;
+    while (m > 1) {
+      size_t p = 0;
+      for (size_t q : {4, 2, 3, 5, 7}) if (m % q == 0) { p = q; break; }
+      if (!p) {
+        p = 11;
+        while (m % p) { p += 2; if (p * p > m) { p = m; break; } }
+      }
+      f->radices.push_back((uint32_t)p);
+      m /= p;
+    }
+  }
+  f->tmpview.c = c; f->tmpview.a = nullptr; f->tmpview.off = 0; f->tmpview.len = 0; f->tmpview.cap = 0;
+  f->tmpview.plan_owned = true;
+  *out = f;
+  return AE_OK;
+}
+ae_status ae_fft_destroy(ae_fft* f) {
+  if (!f) return AE_OK;
+  cudaSetDevice(f->c->dev);
+  dev_free(f->c, f->scratch);
+  if (f->tmp) { flush_vec(&f->tmpview); alloc_unref(f->c, f->tmp); }
+  delete f;
+  return AE_OK;
+}
+size_t ae_fft_len(const ae_fft* f) { return f ? f->len : 0; }
+ae_status ae_fft_set_compat(ae_fft* f, int compat) {
+  if (!f || (compat != AE_COMPAT_REFERENCE && compat != AE_COMPAT_CORRECTED)) return fail(AE_EARG, "bad compat");
+  f->compat = compat;
+  return AE_OK;
+}
+
+ae_status ae_fft_exec(ae_fft* f, int dir, ae_vec* in, ae_vec* out, int scale_kind, float x, size_t howmany) {
+  if (!f || !in) return fail(AE_EARG, "null");
+  if (dir != AE_FFT_FWD && dir != AE_FFT_BWD) return fail(AE_EARG, "bad direction");
+  if (scale_kind < 0 || scale_kind > 3) return fail(AE_EARG, "bad scale kind");
+  if (in->len != f->len * howmany) return fail(AE_ELEN, "Input and FFT must be the same length");  // src/fft.rs:163-167
+  if (out && out->len != in->len) return fail(AE_ELEN, "Input and FFT must be the same length");
+  cudaSetDevice(f->c->dev);
+  if (!out || out == in || (out->a == in->a && out->off == in->off)) {
+    TRY(before_write(in));
+    return fft_run(f, dir, vptr(in), vptr(in), scale_kind, x, howmany);
+  }
+  if (out->a == in->a) return fail(AE_EARG, "fwd/bwd: output overlaps input");
+  TRY(before_read(in));
+  TRY(before_write(out));
+  return fft_run(f, dir, vptr(in), vptr(out), scale_kind, x, howmany);
+}
+
+ae_status ae_fft_exec_tmp(ae_fft* f, int dir, ae_vec* in, int scale_kind, float x, size_t howmany, ae_vec** view) {
+  if (!f || !in || !view) return fail(AE_EARG, "null");
+  if (dir != AE_FFT_FWD && dir != AE_FFT_BWD) return fail(AE_EARG, "bad direction");
+  if (in->len != f->len * howmany) return fail(AE_ELEN, "Input and FFT must be the same length");  // src/fft.rs:207-211
+  cudaSetDevice(f->c->dev);
+  const size_t need = in->len;
+  if (f->tmp) TRY(before_write(&f->tmpview));
+  if (f->tmp_elems < need || !f->tmp) {
+    if (f->tmp) alloc_unref(f->c, f->tmp);
+    ae_status st;
+    f->tmp = alloc_new(f->c, std::max<size_t>(need, 1) * sizeof(float2), &st);
+    if (!f->tmp) { f->tmp_elems = 0; return st; }
+    f->tmp_elems = need;
+  }
+  f->tmpview.a = f->tmp; f->tmpview.off = 0; f->tmpview.len = need; f->tmpview.cap = need;
+  if (in->a == f->tmp) return fail(AE_EARG, "tfwd/tbwd: input is the plan's own scratch");
+  TRY(before_read(in));
+  TRY(fft_run(f, dir, vptr(in), vptr(&f->tmpview), scale_kind, x, howmany));
+  *view = &f->tmpview;
+  return AE_OK;
+}
+
+static ae_status vec_fft_onfly(ae_vec* v, int dir, int scale_kind, float x, int compat) {
+  if (!v) return fail(AE_EARG, "null");
+  if (v->len == 0) return AE_OK;
+  ae_fft* f;
+  TRY(ae_fft_create(v->len, &f));  // Cfft::with_len(self.len()) per call (src/vecops.rs:302)
+  ae_fft_set_compat(f, compat);
+  ae_status st = ae_fft_exec(f, dir, v, nullptr, scale_kind, x, 1);
+  ae_fft_destroy(f);
+  return st;
+}
+ae_status ae_vec_fft(ae_vec* v, int scale_kind, float x, int compat) { return vec_fft_onfly(v, AE_FFT_FWD, scale_kind, x, compat); }
+ae_status ae_vec_ifft(ae_vec* v, int scale_kind, float x, int compat) { return vec_fft_onfly(v, AE_FFT_BWD, scale_kind, x, compat); }
+
+}  // extern "C"
+
+// =================================================================================================
+// FIR
+// =================================================================================================
+struct ae_fir {
+  Ctx* c;
+  size_t ntaps;
+  int tp;         // taps rounded up to a multiple of 8
+  int mode;       // resolved: DIRECT or OVERLAP_SAVE
+  float2* d_taps; // tp entries, zero padded
+  float2* d_hist; // tp-1 entries, newest last
+  float2* d_hist2;
+  size_t nfft;
+  float2* d_H;
+  float2* d_tw;
+};
+
+extern "C" {
+
+ae_status ae_fir_create(const ae_cf32* taps_host, size_t ntaps, int mode, ae_fir** out) {
+  if (!out || !taps_host) return fail(AE_EARG, "null");
+  if (ntaps == 0) return fail(AE_EARG, "FIR needs at least one tap");
+  if (mode < AE_FIR_AUTO || mode > AE_FIR_OVERLAP_SAVE) return fail(AE_EARG, "bad FIR mode");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  size_t nfft = 1024;
+  while (nfft < 4 * ntaps) nfft <<= 1;
+  const bool os_ok = fir_os_supported(nfft) && ntaps <= nfft / 2;
+  const bool direct_ok = ntaps <= 4096;
+  if (mode == AE_FIR_AUTO) mode = (ntaps <= 24 || !os_ok) ? AE_FIR_DIRECT : AE_FIR_OVERLAP_SAVE;
+  if (mode == AE_FIR_DIRECT && !direct_ok) return fail(AE_EARG, "direct-form FIR supports at most 4096 taps");
+  if (mode == AE_FIR_OVERLAP_SAVE && !os_ok) return fail(AE_EARG, "overlap-save FIR supports at most 4096 taps");
+  ae_fir* f = new ae_fir;
+  f->c = c; f->ntaps = ntaps; f->tp = (int)(((ntaps + 7) / 8) * 8); f->mode = mode;
+  f->d_taps = f->d_hist = f->d_hist2 = f->d_H = f->d_tw = nullptr; f->nfft = nfft;
+  void* p;
+  std::vector<float2> h(f->tp, make_float2(0.f, 0.f));
+  for (size_t i = 0; i < ntaps; ++i) h[i] = make_float2(taps_host[i].re, taps_host[i].im);
+  TRY(dev_alloc(c, f->tp * sizeof(float2), &p)); f->d_taps = (float2*)p;
+  CK(cudaMemcpyAsync(f->d_taps, h.data(), f->tp * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  TRY(dev_alloc(c, f->tp * sizeof(float2), &p)); f->d_hist = (float2*)p;
+  TRY(dev_alloc(c, f->tp * sizeof(float2), &p)); f->d_hist2 = (float2*)p;
+  CK(cudaMemsetAsync(f->d_hist, 0, f->tp * sizeof(float2), c->stream));
+  CK(cudaMemsetAsync(f->d_hist2, 0, f->tp * sizeof(float2), c->stream));
+  if (mode == AE_FIR_OVERLAP_SAVE) {
+    TRY(get_twiddles(c, nfft, &f->d_tw));
+    std::vector<float2> hp(nfft, make_float2(0.f, 0.f));
+    for (size_t i = 0; i < ntaps; ++i) hp[i] = h[i];
+    TRY(dev_alloc(c, nfft * sizeof(float2), &p)); f->d_H = (float2*)p;
+    CK(cudaMemcpyAsync(f->d_H, hp.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+    // H = DFT(h) / nfft  (the 1/nfft of the forward/inverse round trip is folded in here)
+    launch_fft_pow2(f->d_H, f->d_H, nfft, 1, f->d_tw, false, true, 1.0f / (float)nfft, c->stream);
+    CKL(1);
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  *out = f;
+  return AE_OK;
+}
+ae_status ae_fir_destroy(ae_fir* f) {
+  if (!f) return AE_OK;
+  cudaSetDevice(f->c->dev);
+  dev_free(f->c, f->d_taps); dev_free(f->c, f->d_hist); dev_free(f->c, f->d_hist2); dev_free(f->c, f->d_H);
+  delete f;
+  return AE_OK;
+}
+size_t ae_fir_ntaps(const ae_fir* f) { return f ? f->ntaps : 0; }
+ae_status ae_fir_reset(ae_fir* f) {
+  if (!f) return fail(AE_EARG, "null");
+  cudaSetDevice(f->c->dev);
+  CK(cudaMemsetAsync(f->d_hist, 0, f->tp * sizeof(float2), f->c->stream));
+  return AE_OK;
+}
+
+ae_status ae_fir_exec(ae_fir* f, ae_vec* in, ae_vec* out, size_t frame_len) {
+  if (!f || !in || !out) return fail(AE_EARG, "null");
+  if (in->len != out->len) return fail(AE_ELEN, "Vectors must have same length");
+  Ctx* c = f->c;
+  cudaSetDevice(c->dev);
+  const size_t n = in->len;
+  if (n == 0) return AE_OK;
+  TRY(before_read(in));
+  TRY(before_write(out));
+  const float2* x = vptr(in);
+  float2* y = vptr(out);
+  void* tmp = nullptr;
+  if (in->a == out->a) {  // blocks read a halo other blocks overwrite: filter from a private copy
+    TRY(dev_alloc(c, n * sizeof(float2), &tmp));
+    CK(cudaMemcpyAsync(tmp, x, n * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+    x = (const float2*)tmp;
+  }
+  int mode = f->mode;
+  if (mode == AE_FIR_DIRECT && frame_len && (frame_len % 8) != 0) {
+    if (!f->d_H) { dev_free(c, tmp); return fail(AE_EARG, "direct-form FIR needs frame_len % 8 == 0"); }
+    mode = AE_FIR_OVERLAP_SAVE;
+  }
+  const float2* hist = frame_len ? nullptr : f->d_hist;
+  if (mode == AE_FIR_DIRECT) launch_fir_direct(x, y, n, f->d_taps, f->tp, hist, frame_len, c->sm_count, c->stream);
+  else launch_fir_overlap_save(x, y, n, f->d_H, f->d_tw, f->nfft, f->ntaps, hist, frame_len, c->stream);
+  CKL(1);
+  if (!frame_len && f->tp > 1) {  // carry the last tp-1 inputs
+    const size_t hl = (size_t)f->tp - 1;
+    if (n >= hl) {
+      CK(cudaMemcpyAsync(f->d_hist, x + (n - hl), hl * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+      CK(cudaMemcpyAsync(f->d_hist2, f->d_hist + n, (hl - n) * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+      CK(cudaMemcpyAsync(f->d_hist2 + (hl - n), x, n * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+      std::swap(f->d_hist, f->d_hist2);
+    }
+  }
+  dev_free(c, tmp);
+  return AE_OK;
+}
+
+// =================================================================================================
+// sampling
+// =================================================================================================
+ae_status ae_interpolate(ae_vec* src, ae_vec* dst, size_t n_between, int compat) {
+  if (!src || !dst) return fail(AE_EARG, "null");
+  if (src->len == 0) return fail(AE_EARG, "called `Option::unwrap()` on a `None` value");  // src/sampling.rs:23
+  if (src->a == dst->a) return fail(AE_EARG, "interpolate: dst aliases src");
+  if (n_between >= (1u << 30)) return fail(AE_EARG, "n_between too large");
+  cudaSetDevice(src->c->dev);
+  const size_t n_out = (src->len - 1) * (n_between + 1) + 1;
+  TRY(before_read(src));
+  TRY(before_write(dst));
+  TRY(vec_reserve(dst, dst->len + n_out));
+  launch_interpolate(vptr(src), src->len, vptr(dst) + dst->len, n_between, compat, src->c->stream);
+  CKL(1);
+  dst->len += n_out;  // appended, like Vec::push
+  return AE_OK;
+}
+static ae_status downsample_impl(ae_vec* src, ae_vec* dst, int strict) {
+  if (!src || !dst) return fail(AE_EARG, "null");
+  if (dst->len == 0) return fail(AE_EARG, "attempt to divide by zero");                       // src/sampling.rs:38
+  if (strict && (src->len % dst->len) != 0) return fail(AE_ELEN, "Only even decimations are supported");  // :32
+  if (src->a == dst->a) return fail(AE_EARG, "downsample: dst aliases src");
+  const size_t dec = src->len / dst->len;
+  if (dst->len > 0 && (dst->len - 1) * dec >= src->len && src->len > 0 && dec > 0) return fail(AE_EIDX, "index out of bounds");
+  if (src->len == 0) return fail(AE_EIDX, "index out of bounds");
+  cudaSetDevice(src->c->dev);
+  TRY(before_read(src));
+  TRY(before_write(dst));
+  launch_downsample_cf32(vptr(src), vptr(dst), dst->len, dec, src->c->stream);
+  CKL(1);
+  return AE_OK;
+}
+ae_status ae_downsample(ae_vec* src, ae_vec* dst, int strict) { return downsample_impl(src, dst, strict); }
+ae_status ae_downsample_sb(ae_vec* src, ae_vec* dst, int strict) {
+  // step_by variant (src/sampling.rs:49-62): zip stops at the shorter side, step_by(0) panics
+  if (src && dst && dst->len && src->len / dst->len == 0) return fail(AE_EARG, "assertion failed: step != 0");
+  return downsample_impl(src, dst, strict);
+}
+ae_status ae_downsample_bits(ae_bits* src, ae_bits* dst, int strict) {
+  if (!src || !dst) return fail(AE_EARG, "null");
+  if (dst->len == 0) return fail(AE_EARG, "attempt to divide by zero");
+  if (strict && (src->len % dst->len) != 0) return fail(AE_ELEN, "Only even decimations are supported");
+  if (src->len == 0) return fail(AE_EIDX, "index out of bounds");
+  const size_t dec = src->len / dst->len;
+  cudaSetDevice(src->c->dev);
+  launch_downsample_u8(bptr(src), bptr(dst), dst->len, dec, src->c->stream);
+  CKL(1);
+  return AE_OK;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// modulation
+// =================================================================================================
+struct ae_mod {
+  Ctx* c;
+  ModTable tab;
+};
+
+extern "C" {
+
+ae_status ae_mod_create(const ae_cf32* table, size_t table_len, ae_mod** out) {
+  if (!out || !table) return fail(AE_EARG, "null");
+  if (table_len != 2 && table_len != 4) return fail(AE_EARG, "Modulation is implemented for [cf32; 2] and [cf32; 4] only");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  ae_mod* m = new ae_mod;
+  m->c = c;
+  m->tab.len = (int)table_len;
+  for (size_t i = 0; i < 4; ++i) m->tab.t[i] = i < table_len ? make_float2(table[i].re, table[i].im) : make_float2(0.f, 0.f);
+  *out = m;
+  return AE_OK;
+}
+ae_status ae_mod_bpsk(ae_mod** out) {
+  const ae_cf32 t[2] = {{1.0f, 1.0f}, {-1.0f, -1.0f}};  // GENERIC_BPSK_TABLE src/modulation.rs:77
+  return ae_mod_create(t, 2, out);
+}
+ae_status ae_mod_qpsk(ae_mod** out) {
+  const ae_cf32 t[4] = {{1.0f, 1.0f}, {-1.0f, 1.0f}, {1.0f, -1.0f}, {-1.0f, -1.0f}};  // src/modulation.rs:87-92
+  return ae_mod_create(t, 4, out);
+}
+ae_status ae_mod_destroy(ae_mod* m) { delete m; return AE_OK; }
+size_t ae_mod_bits_per_symbol(const ae_mod* m) { return m ? (m->tab.len == 2 ? 1 : 2) : 0; }
+
+static ae_status modulate_impl(ae_mod* m, ae_bits* bits, ae_vec* out, bool collect) {
+  if (!m || !bits || !out) return fail(AE_EARG, "null");
+  const size_t bps = ae_mod_bits_per_symbol(m);
+  cudaSetDevice(m->c->dev);
+  const size_t nsym_full = bits->len / bps;
+  const bool ragged = (bits->len % bps) != 0;
+  size_t n_out;
+  if (collect) {
+    // chunks(BPS) yields a short last chunk; QPSK index() then reads bits[1] out of bounds (:24)
+    if (ragged) return fail(AE_EIDX, "index out of bounds: the len is 1 but the index is 1");
+    n_out = nsym_full;
+    TRY(before_write(out));
+    TRY(flush_vec(out));
+    TRY(vec_reserve(out, n_out));
+    out->len = n_out;
+  } else {
+    TRY(before_write(out));
+    TRY(flush_vec(out));
+    n_out = std::min(out->len, nsym_full + (ragged ? 1 : 0));  // zip truncates (:123-131)
+    if (ragged && n_out > nsym_full) return fail(AE_EIDX, "index out of bounds: the len is 1 but the index is 1");
+  }
+  launch_modulate(m->tab, bptr(bits), bits->len, vptr(out), n_out, m->c->d_err, m->c->stream);
+  if (n_out) CKL(1);
+  return AE_OK;
+}
+ae_status ae_mod_modulate(ae_mod* m, ae_bits* bits, ae_vec* out) { return modulate_impl(m, bits, out, true); }
+ae_status ae_mod_modulate_into(ae_mod* m, ae_bits* bits, ae_vec* out) { return modulate_impl(m, bits, out, false); }
+
+ae_status ae_mod_demod(ae_mod* m, ae_vec* symbols, ae_bits* out, int compat) {
+  if (!m || !symbols || !out) return fail(AE_EARG, "null");
+  const size_t bps = ae_mod_bits_per_symbol(m);
+  cudaSetDevice(m->c->dev);
+  TRY(before_read(symbols));
+  const size_t add = symbols->len * bps;
+  TRY(bits_reserve(out, out->len + add));
+  launch_demod(m->tab, vptr(symbols), symbols->len, bptr(out) + out->len, compat, m->c->stream);
+  if (symbols->len) CKL(1);
+  out->len += add;  // output.push / extend (:51-53, :142)
+  return AE_OK;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// noise
+// =================================================================================================
+struct ae_awgn {
+  Ctx* c;
+  float power, scale;
+  uint64_t seed, stream_id, offset;
+};
+
+extern "C" {
+
+ae_status ae_awgn_create(float power, uint64_t seed, ae_awgn** out) {
+  if (!out) return fail(AE_EARG, "null");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  ae_awgn* g = new ae_awgn;
+  g->c = c; g->power = power; g->scale = sqrtf(power);  // src/noise.rs:35
+  g->seed = seed; g->stream_id = 0; g->offset = 0;
+  *out = g;
+  return AE_OK;
+}
+ae_status ae_awgn_generator(ae_awgn** out) { return ae_awgn_create(1.0f, 815ull, out); }  // src/noise.rs:6-11
+ae_status ae_awgn_destroy(ae_awgn* g) { delete g; return AE_OK; }
+ae_status ae_awgn_set_power(ae_awgn* g, float power) {
+  if (!g) return fail(AE_EARG, "null");
+  g->power = power; g->scale = sqrtf(power);
+  return AE_OK;
+}
+ae_status ae_awgn_set_stream_id(ae_awgn* g, uint64_t id) {
+  if (!g) return fail(AE_EARG, "null");
+  g->stream_id = id;
+  return AE_OK;
+}
+ae_status ae_awgn_seek(ae_awgn* g, uint64_t off) {
+  if (!g) return fail(AE_EARG, "null");
+  g->offset = off;
+  return AE_OK;
+}
+uint64_t ae_awgn_tell(const ae_awgn* g) { return g ? g->offset : 0; }
+
+ae_status ae_awgn_fill(ae_awgn* g, ae_vec* target) {
+  if (!g || !target) return fail(AE_EARG, "null");
+  cudaSetDevice(g->c->dev);
+  TRY(before_write(target));
+  TRY(flush_vec(target));
+  const size_t n = target->cap - target->len;  // while len < capacity { push(next()) }
+  launch_awgn_fill(vptr(target) + target->len, n, g->scale, g->seed, g->stream_id, g->offset, g->c->stream);
+  if (n) CKL(1);
+  target->len = target->cap;
+  g->offset += n;
+  return AE_OK;
+}
+ae_status ae_awgn_apply(ae_awgn* g, ae_vec* signal, int compat) {
+  if (!g || !signal) return fail(AE_EARG, "null");
+  cudaSetDevice(g->c->dev);
+  TRY(before_write(signal));
+  TRY(flush_vec(signal));
+  launch_awgn_apply(vptr(signal), signal->len, g->scale, compat == AE_COMPAT_REFERENCE ? 1 : 0, g->seed, g->stream_id,
+                    g->offset, g->c->stream);
+  if (signal->len) CKL(1);
+  g->offset += signal->len;
+  return AE_OK;
+}
+ae_status ae_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  if (!ctr || !key || !out) return fail(AE_EARG, "null");
+  uint32_t o[4];
+  philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], o);
+  for (int i = 0; i < 4; ++i) out[i] = o[i];
+  return AE_OK;
+}
+
+// =================================================================================================
+// sequence
+// =================================================================================================
+ae_status ae_mseq_expand(uint64_t seed, size_t len, ae_bits* out) {
+  if (!out) return fail(AE_EARG, "null");
+  if (len > 64) return fail(AE_EARG, "attempt to shift right with overflow");  // src/sequence.rs:20, i >= 64
+  cudaSetDevice(out->c->dev);
+  TRY(bits_reserve(out, len));
+  out->len = len;
+  launch_expand(seed, len, bptr(out), out->c->stream);
+  if (len) CKL(1);
+  return AE_OK;
+}
+ae_status ae_mseq_generate(const uint8_t* init_host, size_t n_init, const uint32_t* back, size_t n_back, size_t len,
+                           ae_bits* out) {
+  if (!out || (!init_host && n_init) || (!back && n_back)) return fail(AE_EARG, "null");
+  Ctx* c = out->c;
+  cudaSetDevice(c->dev);
+  const size_t total = std::max(len, n_init);  // generate() never truncates init (src/sequence.rs:48)
+  TRY(bits_reserve(out, total));
+  out->len = total;
+  if (len > n_init) {
+    uint32_t deg = 0;
+    for (size_t t = 0; t < n_back; ++t) {
+      if (back[t] == 0) return fail(AE_EIDX, "index out of bounds: generator reads the element it is producing");
+      deg = std::max(deg, back[t]);
+    }
+    if (deg > n_init) return fail(AE_EIDX, "attempt to subtract with overflow: init shorter than the deepest tap");
+    if (deg > 64) return fail(AE_EARG, "tap offsets above 64 are not supported");
+    if (deg == 0) {
+      // no taps: every generated element is (empty sum) % 2 = 0
+      CK(cudaMemsetAsync(bptr(out) + n_init, 0, len - n_init, c->stream));
+    } else {
+      const size_t base = n_init - deg;
+      uint64_t poly_low = 0, state = 0;
+      for (size_t t = 0; t < n_back; ++t) poly_low ^= 1ull << (deg - back[t]);
+      for (uint32_t j = 0; j < deg; ++j) state |= (uint64_t)(init_host[base + j] & 1u) << j;
+      launch_mseq(state, poly_low, (int)deg, len - base, bptr(out) + base, c->stream);
+      CKL(1);
+    }
+  }
+  if (n_init) {  // init is returned verbatim, whatever byte values it holds
+    CK(cudaMemcpyAsync(bptr(out), init_host, n_init, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return AE_OK;
+}
+
+// =================================================================================================
+// statistics
+// =================================================================================================
+ae_status ae_stats_alloc(ae_stats** d) {
+  if (!d) return fail(AE_EARG, "null");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  CK(cudaMalloc((void**)d, sizeof(ae_stats)));
+  CK(cudaMemsetAsync(*d, 0, sizeof(ae_stats), c->stream));
+  return AE_OK;
+}
+ae_status ae_stats_free(ae_stats* d) {
+  if (d) CK(cudaFree(d));
+  return AE_OK;
+}
+ae_status ae_stats_zero(ae_stats* d) {
+  Ctx* c;
+  TRY(get_ctx(&c));
+  if (!d) return fail(AE_EARG, "null");
+  CK(cudaMemsetAsync(d, 0, sizeof(ae_stats), c->stream));
+  return AE_OK;
+}
+ae_status ae_stats_read(const ae_stats* d, ae_stats* host) {
+  Ctx* c;
+  TRY(get_ctx(&c));
+  if (!d || !host) return fail(AE_EARG, "null");
+  CK(cudaMemcpyAsync(host, d, sizeof(ae_stats), cudaMemcpyDeviceToHost, c->stream));
+  return ae_sync();
+}
+ae_status ae_count_bit_errors(ae_bits* a, ae_bits* b, ae_stats* d) {
+  if (!a || !b || !d) return fail(AE_EARG, "null");
+  if (a->len != b->len) return fail(AE_ELEN, "Vectors must have same length");
+  cudaSetDevice(a->c->dev);
+  launch_bit_errors(bptr(a), bptr(b), a->len, d, a->c->sm_count, a->c->stream);
+  if (a->len) CKL(1);
+  return AE_OK;
+}
+ae_status ae_evm_accumulate(ae_vec* act, ae_vec* ref, ae_stats* d) {
+  if (!act || !ref || !d) return fail(AE_EARG, "null");
+  if (act->len != ref->len) return fail(AE_ELEN, "Input slices/vectors must be same length");  // src/lib.rs:34
+  cudaSetDevice(act->c->dev);
+  TRY(before_read(act));
+  TRY(before_read(ref));
+  launch_evm_acc(vptr(act), vptr(ref), act->len, d, act->c->sm_count, act->c->stream);
+  if (act->len) CKL(1);
+  return AE_OK;
+}
+
+// =================================================================================================
+// fused chains
+// =================================================================================================
+ae_status ae_modem_fused(ae_mod* m, ae_awgn* g, ae_bits* bits_in, ae_bits* bits_out, ae_stats* d, int compat) {
+  if (!m || !g || !bits_in || !bits_out) return fail(AE_EARG, "null");
+  const size_t bps = ae_mod_bits_per_symbol(m);
+  if (bits_in->len % bps) return fail(AE_EIDX, "index out of bounds: the len is 1 but the index is 1");
+  cudaSetDevice(m->c->dev);
+  TRY(bits_reserve(bits_out, bits_in->len));
+  bits_out->len = bits_in->len;
+  launch_modem_fused(m->tab, bptr(bits_in), bits_in->len, bptr(bits_out), g->scale, compat == AE_COMPAT_REFERENCE ? 1 : 0,
+                     g->seed, g->stream_id, g->offset, compat, d, m->c->d_err, m->c->sm_count, m->c->stream);
+  if (bits_in->len) CKL(1);
+  g->offset += bits_in->len / bps;
+  return AE_OK;
+}
+
+}  // extern "C"
+
+struct ae_chain {
+  Ctx* c;
+  size_t n, ntaps;
+  int scale_kind, compat;
+  float x, s;
+  bool fused;
+  float2 *d_tw, *d_window, *d_taps;
+  ae_fft* fft;
+  ae_fir* fir;
+  ae_mod* qpsk;
+  // host pipeline
+  float2* d_in[3];
+  uint8_t* d_out[3];
+  size_t chunk_frames;
+};
+
+extern "C" {
+
+ae_status ae_chain_create(size_t fft_len, const ae_cf32* taps_host, size_t ntaps, int scale_kind, float x, int compat,
+                          ae_chain** out) {
+  if (!out || !taps_host) return fail(AE_EARG, "null");
+  if (fft_len == 0 || ntaps == 0) return fail(AE_EARG, "empty chain");
+  if (scale_kind < 0 || scale_kind > 3) return fail(AE_EARG, "bad scale kind");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  ae_chain* ch = new ae_chain;
+  std::memset(ch, 0, sizeof(*ch));
+  ch->c = c; ch->n = fft_len; ch->ntaps = ntaps; ch->scale_kind = scale_kind; ch->x = x; ch->compat = compat;
+  ch->s = scale_factor(scale_kind, fft_len, x);
+  ch->fused = chain_fused_supported(fft_len, ntaps);
+  ae_status st = ae_fft_create(fft_len, &ch->fft);
+  if (st == AE_OK) { ae_fft_set_compat(ch->fft, compat); st = ae_fir_create(taps_host, ntaps, AE_FIR_AUTO, &ch->fir); }
+  if (st == AE_OK) st = ae_mod_qpsk(&ch->qpsk);
+  if (st != AE_OK) { ae_chain_destroy(ch); return st; }
+  if (ch->fused) {
+    TRY(get_twiddles(c, fft_len, &ch->d_tw));
+    // window[m] = s * sum_k h[k] exp(-sgn 2 pi i m k / N), sgn = exponent sign of Cfft::fwd
+    const double sgn = (compat == AE_COMPAT_REFERENCE) ? +1.0 : -1.0;
+    std::vector<float2> w(fft_len), h(ntaps);
+    for (size_t m = 0; m < fft_len; ++m) {
+      double ar = 0, ai = 0;
+      for (size_t k = 0; k < ntaps; ++k) {
+        const double a = -sgn * 2.0 * M_PI * (double)((m * k) % fft_len) / (double)fft_len;
+        const double cr = std::cos(a), ci = std::sin(a);
+        ar += taps_host[k].re * cr - taps_host[k].im * ci;
+        ai += taps_host[k].re * ci + taps_host[k].im * cr;
+      }
+      w[m] = make_float2((float)(ar * (double)ch->s), (float)(ai * (double)ch->s));
+    }
+    for (size_t k = 0; k < ntaps; ++k) h[k] = make_float2(taps_host[k].re, taps_host[k].im);
+    void* p;
+    TRY(dev_alloc(c, fft_len * sizeof(float2), &p)); ch->d_window = (float2*)p;
+    TRY(dev_alloc(c, ntaps * sizeof(float2), &p)); ch->d_taps = (float2*)p;
+    CK(cudaMemcpyAsync(ch->d_window, w.data(), fft_len * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(ch->d_taps, h.data(), ntaps * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  *out = ch;
+  return AE_OK;
+}
+ae_status ae_chain_destroy(ae_chain* ch) {
+  if (!ch) return AE_OK;
+  cudaSetDevice(ch->c->dev);
+  ae_fft_destroy(ch->fft); ae_fir_destroy(ch->fir); ae_mod_destroy(ch->qpsk);
+  dev_free(ch->c, ch->d_window); dev_free(ch->c, ch->d_taps);
+  for (int i = 0; i < 3; ++i) { if (ch->d_in[i]) cudaFree(ch->d_in[i]); if (ch->d_out[i]) cudaFree(ch->d_out[i]); }
+  delete ch;
+  return AE_OK;
+}
+
+ae_status ae_chain_exec_unfused(ae_chain* ch, ae_vec* in, ae_bits* bits_out, ae_vec* symbols_out) {
+  if (!ch || !in || !bits_out) return fail(AE_EARG, "null");
+  if (in->len % ch->n) return fail(AE_ELEN, "Input and FFT must be the same length");
+  cudaSetDevice(ch->c->dev);
+  const size_t frames = in->len / ch->n;
+  ae_vec *X = nullptr, *Y = symbols_out;
+  TRY(ae_vec_alloc(in->len, in->len, &X));
+  ae_status st = AE_OK;
+  if (!Y) st = ae_vec_alloc(in->len, in->len, &Y);
+  else if (Y->len != in->len) st = fail(AE_ELEN, "Vectors must have same length");
+  if (st == AE_OK) st = ae_fft_exec(ch->fft, AE_FFT_FWD, in, X, ch->scale_kind, ch->x, frames);
+  if (st == AE_OK) st = ae_fir_exec(ch->fir, X, Y, ch->n);
+  if (st == AE_OK) { bits_out->len = 0; st = ae_mod_demod(ch->qpsk, Y, bits_out, ch->compat); }
+  ae_vec_free(X);
+  if (Y != symbols_out) ae_vec_free(Y);
+  return st;
+}
+
+ae_status ae_chain_exec(ae_chain* ch, ae_vec* in, ae_bits* bits_out) {
+  if (!ch || !in || !bits_out) return fail(AE_EARG, "null");
+  if (in->len % ch->n) return fail(AE_ELEN, "Input and FFT must be the same length");
+  if (!ch->fused) return ae_chain_exec_unfused(ch, in, bits_out, nullptr);
+  Ctx* c = ch->c;
+  cudaSetDevice(c->dev);
+  const size_t frames = in->len / ch->n;
+  TRY(before_read(in));
+  TRY(bits_reserve(bits_out, 2 * in->len));
+  bits_out->len = 2 * in->len;
+  const bool inverse = (ch->compat == AE_COMPAT_REFERENCE);
+  launch_chain_fused(vptr(in), bptr(bits_out), ch->n, frames, ch->d_window, ch->d_taps, ch->ntaps, ch->d_tw, inverse, ch->s,
+                     ch->compat, c->stream);
+  if (frames) CKL(1);
+  return AE_OK;
+}
+
+ae_status ae_chain_exec_host(ae_chain* ch, const ae_cf32* host_in, size_t n_samples, uint8_t* host_bits) {
+  if (!ch || (!host_in && n_samples) || (!host_bits && n_samples)) return fail(AE_EARG, "null");
+  if (n_samples % ch->n) return fail(AE_ELEN, "Input and FFT must be the same length");
+  if (!ch->fused) return fail(AE_EARG, "host pipeline needs the fused chain (power-of-two FFT length 256..4096)");
+  Ctx* c = ch->c;
+  cudaSetDevice(c->dev);
+  const size_t frames = n_samples / ch->n;
+  // 3-deep pipeline of (H2D, kernel, D2H) on three streams; chunk = 64 MiB of input
+  if (!ch->chunk_frames) {
+    ch->chunk_frames = std::max<size_t>(1, ((size_t)64 << 20) / (ch->n * sizeof(float2)));
+    for (int i = 0; i < 3; ++i) {
+      CK(cudaMalloc((void**)&ch->d_in[i], ch->chunk_frames * ch->n * sizeof(float2)));
+      CK(cudaMalloc((void**)&ch->d_out[i], ch->chunk_frames * ch->n * 2));
+    }
+  }
+  const bool inverse = (ch->compat == AE_COMPAT_REFERENCE);
+  // order the pipeline after work already queued on the context stream
+  cudaEvent_t ev;
+  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CK(cudaEventRecord(ev, c->stream));
+  for (int i = 0; i < 3; ++i) CK(cudaStreamWaitEvent(c->pipe[i], ev, 0));
+  size_t done = 0;
+  int slot = 0;
+  while (done < frames) {
+    const size_t fc = std::min(ch->chunk_frames, frames - done);
+    cudaStream_t st = c->pipe[slot];
+    CK(cudaMemcpyAsync(ch->d_in[slot], host_in + done * ch->n, fc * ch->n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    launch_chain_fused(ch->d_in[slot], ch->d_out[slot], ch->n, fc, ch->d_window, ch->d_taps, ch->ntaps, ch->d_tw, inverse,
+                       ch->s, ch->compat, st);
+    CKL(1);
+    CK(cudaMemcpyAsync(host_bits + 2 * done * ch->n, ch->d_out[slot], fc * ch->n * 2, cudaMemcpyDeviceToHost, st));
+    done += fc;
+    slot = (slot + 1) % 3;
+  }
+  for (int i = 0; i < 3; ++i) {
+    CK(cudaEventRecord(ev, c->pipe[i]));
+    CK(cudaStreamWaitEvent(c->stream, ev, 0));
+  }
+  CK(cudaEventDestroy(ev));
+  for (int i = 0; i < 3; ++i) CK(cudaStreamSynchronize(c->pipe[i]));
+  return AE_OK;
+}
+
+ae_status ae_ofdm_chain(size_t fft_len, size_t frames, uint64_t first_frame_id, float noise_power, uint64_t noise_seed,
+                        int compat, ae_bits* tx_bits, ae_bits* rx_bits, ae_stats* d) {
+  if (!ofdm_supported(fft_len)) return fail(AE_EARG, "ofdm chain supports power-of-two FFT lengths 512..4096");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  float2* tw;
+  TRY(get_twiddles(c, fft_len, &tw));
+  const size_t nbits = 2 * fft_len * frames;
+  if (tx_bits) { TRY(bits_reserve(tx_bits, nbits)); tx_bits->len = nbits; }
+  if (rx_bits) { TRY(bits_reserve(rx_bits, nbits)); rx_bits->len = nbits; }
+  launch_ofdm_chain(fft_len, frames, first_frame_id, sqrtf(noise_power), compat == AE_COMPAT_REFERENCE ? 1 : 0, noise_seed, tw,
+                    compat, tx_bits ? bptr(tx_bits) : nullptr, rx_bits ? bptr(rx_bits) : nullptr, d, c->stream);
+  if (frames) CKL(1);
+  return AE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,292 @@
+// chain.cu — fused chains (sm_100a):
+//   K14 fft_fir_demod : per frame Cfft::fwd(scale) -> FIR (zero state per frame) -> QPSK demod_naive
+//                       8 B in + 2 B out per sample; nothing else touches HBM.
+//   K12 ofdm_chain    : M-sequence -> QPSK -> bwd FFT(SN) -> AWGN -> fwd FFT(SN) -> demod -> BER/EVM
+//
+// K14 algorithm.  A direct 64-tap FIR costs 512 flop/sample and would make the
+// chain FP32-bound at ~1/4 of the HBM roofline.  Instead use the convolution theorem on the
+// transform itself.  With X = DFT_s(x) (exponent sign s), the CIRCULAR convolution of X with h is
+//     C[n] = sum_k h[k] X[(n-k) mod N] = DFT_s( x .* w )[n],   w[m] = sum_k h[k] exp(-s 2 pi i m k/N),
+// and the linear, zero-state FIR the reference semantics ask for differs from it only in the first
+// T-1 outputs:
+//     y[n] = C[n] - sum_{k=n+1}^{T-1} h[k] X[N + n - k]        (n < T-1),
+// which needs the last T-1 bins of the plain transform.  So each frame runs two in-register FFTs
+// (A = DFT(x), B = DFT(x .* w)), a triangular fix-up of T(T-1)/2 complex MACs, and the exact
+// reference hard decision on the result:  ~2*50 + 6 + 16 flop/sample instead of 562.
+#include "fft_device.cuh"
+#include "internal.h"
+
+namespace ae {
+
+template <int N>
+struct ChainLaunch {
+  static constexpr int T = FftCfg<N>::T;
+  static constexpr int F = T >= 256 ? 1 : (256 / T);
+  static constexpr int THREADS = F * T;
+};
+
+template <int N, bool INV>
+__global__ void __launch_bounds__(ChainLaunch<N>::THREADS)
+chain_fused_kernel(const float2* __restrict__ x, uint8_t* __restrict__ bits, size_t frames, const float2* __restrict__ window,
+                   const float2* __restrict__ taps, int ntaps, const float2* __restrict__ tw, float scale, int compat) {
+  using C = FftCfg<N>;
+  using LC = ChainLaunch<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [taps: ntaps][per frame: fft buffer SMEM_ELEMS | tail: ntaps]
+  float2* hs = reinterpret_cast<float2*>(smem_raw);
+  const int f = threadIdx.x / C::T;
+  const int t = threadIdx.x % C::T;
+  float2* sm = hs + ntaps + (size_t)f * (C::SMEM_ELEMS + ntaps);
+  float2* tail = sm + C::SMEM_ELEMS;  // tail[i] = scale * A[N - (ntaps-1) + i]
+  for (int i = threadIdx.x; i < ntaps; i += LC::THREADS) hs[i] = __ldg(taps + i);
+  __syncthreads();
+  const size_t frame = (size_t)blockIdx.x * LC::F + f;
+  if (frame >= frames) return;
+  const float2* src = x + frame * N;
+  const int tm1 = ntaps - 1;
+
+  float2 a[16], b[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) a[m] = ld_stream(src + t + m * C::T);
+#pragma unroll
+  for (int m = 0; m < 16; ++m) b[m] = cx_mul(a[m], __ldg(window + t + m * C::T));
+
+  // A = DFT(x): only its last T-1 bins are kept (scaled like Cfft::fwd's output)
+  fft_frame<N, INV>(a, sm, tw, t, f);
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const int pos = t + m * C::T;
+    if (pos >= N - tm1) tail[pos - (N - tm1)] = cx_scale_exact(a[m], scale);
+  }
+  frame_sync<C::T>(f);  // tail visible; everyone is past the last read of sm
+  // B = DFT(x .* w) = circular convolution of scale*X with h
+  fft_frame<N, INV>(b, sm, tw, t, f);
+
+  float2 tab[4] = {make_float2(1.0f, 1.0f), make_float2(-1.0f, 1.0f), make_float2(1.0f, -1.0f), make_float2(-1.0f, -1.0f)};
+  uint8_t* out = bits + 2 * frame * (size_t)N;
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const int n = t + m * C::T;
+    float2 yv = b[m];
+    if (n < tm1) {  // wrap-around terms of the circular convolution
+      float2 acc = make_float2(0.0f, 0.0f);
+      for (int k = n + 1; k <= tm1; ++k) cx_fma(acc, hs[k], tail[n - k + tm1]);
+      yv = cx_sub(yv, acc);
+    }
+    const unsigned idx = demod_index<4>(yv, tab);  // src/modulation.rs:33-56
+    const unsigned b0 = idx & 1u;
+    const unsigned b1 = compat == AE_COMPAT_REFERENCE ? (idx & 2u) : ((idx >> 1) & 1u);
+    *reinterpret_cast<uchar2*>(out + 2 * n) = make_uchar2((unsigned char)b0, (unsigned char)b1);
+  }
+}
+
+bool chain_fused_supported(size_t nfft, size_t ntaps) {
+  return nfft >= 256 && nfft <= 4096 && (nfft & (nfft - 1)) == 0 && ntaps >= 1 && ntaps <= nfft;
+}
+
+template <int N>
+static void launch_chain_n(const float2* x, uint8_t* bits, size_t frames, const float2* window, const float2* taps,
+                           size_t ntaps, const float2* tw, bool inverse, float scale, int compat, cudaStream_t st) {
+  using LC = ChainLaunch<N>;
+  const size_t smem = (ntaps + (size_t)LC::F * (FftCfg<N>::SMEM_ELEMS + ntaps)) * sizeof(float2);
+  const unsigned grid = (unsigned)((frames + LC::F - 1) / LC::F);
+  if (inverse) {
+    cudaFuncSetAttribute(chain_fused_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    chain_fused_kernel<N, true><<<grid, LC::THREADS, smem, st>>>(x, bits, frames, window, taps, (int)ntaps, tw, scale, compat);
+  } else {
+    cudaFuncSetAttribute(chain_fused_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    chain_fused_kernel<N, false><<<grid, LC::THREADS, smem, st>>>(x, bits, frames, window, taps, (int)ntaps, tw, scale, compat);
+  }
+}
+
+void launch_chain_fused(const float2* x, uint8_t* bits, size_t nfft, size_t frames, const float2* window, const float2* taps,
+                        size_t ntaps, const float2* tw, bool inverse, float scale, int compat, cudaStream_t st) {
+  if (frames == 0) return;
+  switch (nfft) {
+#define AE_CASE(NN) case NN: launch_chain_n<NN>(x, bits, frames, window, taps, ntaps, tw, inverse, scale, compat, st); break;
+    AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096)
+#undef AE_CASE
+    default: break;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K12 OFDM-like chain (BASELINE config 5).  One frame per frame slot:
+//   bits   : LTE x1 M-sequence x[n] = (x[n-28] + x[n-31]) % 2 (src/sequence.rs:42) seeded with
+//            expand(frame_id + 1, 31) (src/sequence.rs:18-21), 2N bits per frame; each thread jumps to
+//            its own 32-bit word with z^(32 t) mod p(z) and emits it, so no thread waits for another.
+//   symbols: QPSK table (src/modulation.rs:87-92), idx = (b1<<1)+b0
+//   tx     : Cfft::bwd with Scale::SN            (src/fft.rs:173-182)
+//   channel: Awgn::apply semantics               (src/noise.rs:53-59), Philox stream = frame id,
+//            block index = position mod N/2, words {0,1} for the lower and {2,3} for the upper half
+//   rx     : Cfft::fwd with Scale::SN, demod_naive, bit errors and EVM partial sums.
+// Compulsory HBM traffic: only the audit bits (4 B/symbol) when requested.
+// -------------------------------------------------------------------------------------------------
+constexpr uint64_t kLteX1PolyLow = (1ull << 0) | (1ull << 3);  // p(z) = z^31 + z^3 + 1  (back offsets 31, 28)
+constexpr int kLteDeg = 31;
+
+__device__ __forceinline__ uint32_t lte_mulz(uint32_t r) {  // r * z mod p, deg 31
+  const bool carry = (r >> 30) & 1u;
+  r = (r << 1) & 0x7fffffffu;
+  return carry ? (r ^ (uint32_t)kLteX1PolyLow) : r;
+}
+__device__ __forceinline__ uint32_t lte_mulmod(uint32_t a, uint32_t b) {
+  uint32_t r = 0;
+#pragma unroll 1
+  for (int i = 0; i < kLteDeg; ++i) {
+    if ((b >> i) & 1u) r ^= a;
+    a = lte_mulz(a);
+  }
+  return r;
+}
+
+template <int N>
+struct OfdmLaunch {
+  static constexpr int T = FftCfg<N>::T;
+  static constexpr int F = T >= 256 ? 1 : (256 / T);
+  static constexpr int THREADS = F * T;
+  static constexpr int WORDS = 2 * N / 32;  // packed bits per frame
+  static constexpr size_t SMEM_PER_FRAME = (size_t)FftCfg<N>::SMEM_ELEMS * sizeof(float2) + WORDS * sizeof(uint32_t);
+};
+
+template <int N, bool FWD_INV>  // FWD_INV: exponent sign of Cfft::fwd is + (compat=reference)
+__global__ void __launch_bounds__(OfdmLaunch<N>::THREADS)
+ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int twice, uint64_t seed, const float2* __restrict__ tw,
+                  int compat, uint8_t* __restrict__ tx_bits, uint8_t* __restrict__ rx_bits, ae_stats* stats) {
+  using C = FftCfg<N>;
+  using LC = OfdmLaunch<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int f = threadIdx.x / C::T;
+  const int t = threadIdx.x % C::T;
+  unsigned char* my = smem_raw + (size_t)f * LC::SMEM_PER_FRAME;
+  float2* sm = reinterpret_cast<float2*>(my);
+  uint32_t* words = reinterpret_cast<uint32_t*>(my + (size_t)C::SMEM_ELEMS * sizeof(float2));
+  const size_t fl = (size_t)blockIdx.x * LC::F + f;
+  if (fl >= frames) return;
+  const uint64_t frame_id = first_frame + fl;
+
+  // ---- M-sequence words.  WORDS = N/16 = T: exactly one 32-bit word per thread ----
+  {
+    const uint32_t state = (uint32_t)((frame_id + 1) & 0x7fffffffull);  // expand(frame_id+1, 31)
+    // z^(32 t) mod p by square-and-multiply on the (small) exponent
+    uint32_t r = 1u, sq = 2u;
+    unsigned e = 32u * (unsigned)t;
+    while (e) {
+      if (e & 1u) r = lte_mulmod(r, sq);
+      sq = lte_mulmod(sq, sq);
+      e >>= 1;
+    }
+    uint32_t w = 0;
+#pragma unroll 1
+    for (int j = 0; j < 31; ++j) {
+      w |= (uint32_t)(__popc(r & state) & 1) << j;
+      r = lte_mulz(r);
+    }
+    // bit 31 of the word: x[n+31] = x[n+3] ^ x[n]
+    w |= (((w >> 3) ^ w) & 1u) << 31;
+    words[t] = w;
+  }
+  frame_sync<C::T>(f);
+
+  const float2 tab[4] = {make_float2(1.0f, 1.0f), make_float2(-1.0f, 1.0f), make_float2(1.0f, -1.0f), make_float2(-1.0f, -1.0f)};
+  float2 v[16];
+  uint32_t txb = 0;  // 2 bits per owned symbol
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const int pos = t + m * C::T;
+    const uint32_t w = words[pos >> 4];
+    const unsigned two = (w >> ((2 * pos) & 31)) & 3u;  // bit0 = b0, bit1 = b1 -> idx = (b1<<1)+b0
+    txb |= two << (2 * m);
+    v[m] = tab[two];
+  }
+  if (tx_bits) {
+    uint8_t* o = tx_bits + 2 * fl * (size_t)N;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int pos = t + m * C::T;
+      const unsigned two = (txb >> (2 * m)) & 3u;
+      *reinterpret_cast<uchar2*>(o + 2 * pos) = make_uchar2((unsigned char)(two & 1u), (unsigned char)(two >> 1));
+    }
+  }
+  const float sn = 1.0f / sqrtf((float)N);  // Scale::SN (src/fft.rs:26)
+  // ---- tx: Cfft::bwd, Scale::SN ----
+  fft_frame<N, !FWD_INV>(v, sm, tw, t, f);
+#pragma unroll
+  for (int m = 0; m < 16; ++m) v[m] = cx_scale_exact(v[m], sn);
+  // ---- channel ----
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    float2 z0, z1;
+    awgn_unit_pair(seed, frame_id, (uint64_t)(t + m * C::T), z0, z1);
+    z0 = cx_scale_exact(z0, noise_scale); z1 = cx_scale_exact(z1, noise_scale);
+    if (twice) { z0 = cx_scale_exact(z0, noise_scale); z1 = cx_scale_exact(z1, noise_scale); }
+    v[m] = cx_add_exact(v[m], z0);
+    v[m + 8] = cx_add_exact(v[m + 8], z1);
+  }
+  // ---- rx: Cfft::fwd, Scale::SN, demod ----
+  frame_sync<C::T>(f);
+  fft_frame<N, FWD_INV>(v, sm, tw, t, f);
+  unsigned long long errs = 0;
+  float e_pow = 0.0f, r_pow = 0.0f;
+  uint8_t* ro = rx_bits ? rx_bits + 2 * fl * (size_t)N : nullptr;
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const float2 y = cx_scale_exact(v[m], sn);
+    const unsigned two = (txb >> (2 * m)) & 3u;
+    const unsigned idx = demod_index<4>(y, tab);
+    errs += __popc((idx ^ two) & 3u);
+    const float dr = y.x - tab[two].x, di = y.y - tab[two].y;
+    e_pow += dr * dr + di * di;
+    r_pow += 2.0f;
+    if (ro) {
+      const int pos = t + m * C::T;
+      const unsigned b1 = compat == AE_COMPAT_REFERENCE ? (idx & 2u) : ((idx >> 1) & 1u);
+      *reinterpret_cast<uchar2*>(ro + 2 * pos) = make_uchar2((unsigned char)(idx & 1u), (unsigned char)b1);
+    }
+  }
+  if (stats) {
+    double e = (double)e_pow, r = (double)r_pow;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      errs += __shfl_xor_sync(0xffffffffu, errs, o);
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+      r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(&stats->bit_errors), errs);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_bits), 32ull * 16ull * 2ull);
+      atomicAdd(&stats->err_pow, e);
+      atomicAdd(&stats->ref_pow, r);
+    }
+  }
+}
+
+bool ofdm_supported(size_t nfft) { return nfft >= 512 && nfft <= 4096 && (nfft & (nfft - 1)) == 0; }
+
+template <int N>
+static void launch_ofdm_n(size_t frames, uint64_t first_frame, float noise_scale, int twice, uint64_t seed, const float2* tw,
+                          int compat, uint8_t* tx_bits, uint8_t* rx_bits, ae_stats* stats, cudaStream_t st) {
+  using LC = OfdmLaunch<N>;
+  const size_t smem = LC::SMEM_PER_FRAME * LC::F;
+  const unsigned grid = (unsigned)((frames + LC::F - 1) / LC::F);
+  if (compat == AE_COMPAT_REFERENCE) {
+    cudaFuncSetAttribute(ofdm_chain_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ofdm_chain_kernel<N, true><<<grid, LC::THREADS, smem, st>>>(frames, first_frame, noise_scale, twice, seed, tw, compat, tx_bits, rx_bits, stats);
+  } else {
+    cudaFuncSetAttribute(ofdm_chain_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ofdm_chain_kernel<N, false><<<grid, LC::THREADS, smem, st>>>(frames, first_frame, noise_scale, twice, seed, tw, compat, tx_bits, rx_bits, stats);
+  }
+}
+
+void launch_ofdm_chain(size_t nfft, size_t frames, uint64_t first_frame, float noise_scale, int twice, uint64_t seed,
+                       const float2* tw, int compat, uint8_t* tx_bits, uint8_t* rx_bits, ae_stats* stats, cudaStream_t st) {
+  if (frames == 0) return;
+  switch (nfft) {
+#define AE_CASE(NN) case NN: launch_ofdm_n<NN>(frames, first_frame, noise_scale, twice, seed, tw, compat, tx_bits, rx_bits, stats, st); break;
+    AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096)
+#undef AE_CASE
+    default: break;
+  }
+}
+
+}  // namespace ae

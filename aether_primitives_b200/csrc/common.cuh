@@ -1,0 +1,113 @@
+// common.cuh — shared device helpers for the aether_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "aether_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace ae {
+
+// device-side deferred error flags (reported by ae_sync)
+enum : int { DEVERR_MOD_INDEX = 1 };
+
+// ---- exact (never contracted) cf32 arithmetic: reproduces rustc/num-complex 0.2 ------------
+// src/vecops.rs:94-155 via num-complex: every * + - / is a separately rounded IEEE op.
+__device__ __forceinline__ float2 cx_scale_exact(float2 a, float s) {
+  return make_float2(__fmul_rn(a.x, s), __fmul_rn(a.y, s));
+}
+__device__ __forceinline__ float2 cx_mul_exact(float2 a, float2 b) {
+  return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)),
+                     __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ float2 cx_div_exact(float2 a, float2 b) {
+  const float n = __fadd_rn(__fmul_rn(b.x, b.x), __fmul_rn(b.y, b.y));
+  const float re = __fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+  const float im = __fsub_rn(__fmul_rn(a.y, b.x), __fmul_rn(a.x, b.y));
+  return make_float2(__fdiv_rn(re, n), __fdiv_rn(im, n));
+}
+__device__ __forceinline__ float2 cx_add_exact(float2 a, float2 b) {
+  return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
+__device__ __forceinline__ float2 cx_sub_exact(float2 a, float2 b) {
+  return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y));
+}
+
+// ---- fast cf32 arithmetic (FMA allowed) for the EVM-tier kernels (FFT, FIR) ----------------
+__device__ __forceinline__ float2 cx_mul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cx_mul_conj(float2 a, float2 b) {  // a * conj(b)
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ float2 cx_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 cx_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ void cx_fma(float2& acc, float2 a, float2 b) {  // acc += a*b
+  acc.x = fmaf(a.x, b.x, acc.x);
+  acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y);
+  acc.y = fmaf(a.y, b.x, acc.y);
+}
+
+// ---- streaming global access (data is touched once: do not pollute L1, evict-first in L2) --
+__device__ __forceinline__ float2 ld_stream(const float2* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float2* p, float2 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+
+// QPSK / generic hard decision, exactly the float expressions of src/modulation.rs:36-49 and
+// :133-140 with Iterator::min_by(partial_cmp.unwrap_or(Greater)) semantics: the later
+// candidate wins iff best > later or the comparison is unordered.
+template <int M>
+__device__ __forceinline__ unsigned demod_index(float2 s, const float2 (&tab)[M]) {
+  float d[M];
+#pragma unroll
+  for (int c = 0; c < M; ++c) {
+    const float dr = __fsub_rn(s.x, tab[c].x), di = __fsub_rn(s.y, tab[c].y);
+    d[c] = __fadd_rn(__fmul_rn(dr, dr), __fmul_rn(di, di));
+  }
+  unsigned best = 0;
+  float bd = d[0];
+#pragma unroll
+  for (int c = 1; c < M; ++c)
+    if (!(bd <= d[c])) { bd = d[c]; best = c; }
+  return best;
+}
+
+// Philox4x32-10 (Salmon et al., Random123).  Known-answer vectors in tests/test_noise.py.
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Box-Muller on two 32-bit words -> two independent N(0,1) f32 (full-precision logf/sincospif)
+__device__ __forceinline__ float2 gauss_pair(uint32_t a, uint32_t b) {
+  const float u1 = __fmaf_rn(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float u2 = __fmaf_rn(__uint2float_rn(b), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+// unit-variance complex normals for the sample PAIR (2*pair, 2*pair+1) of a stream
+__device__ __forceinline__ void awgn_unit_pair(uint64_t seed, uint64_t stream, uint64_t pair, float2& z0, float2& z1) {
+  uint32_t o[4];
+  philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)stream, (uint32_t)(stream >> 32),
+                (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  z0 = gauss_pair(o[0], o[1]);
+  z1 = gauss_pair(o[2], o[3]);
+}
+
+}  // namespace ae

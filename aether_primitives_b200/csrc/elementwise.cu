@@ -1,0 +1,610 @@
+// elementwise.cu — HBM-bound element-wise kernels of the cf32 path (sm_100a):
+//   K1  vecops_fused      src/vecops.rs:94-182  (op-tape interpreter, one pass for a whole chain)
+//   K5  downsample        src/sampling.rs:28-62
+//   K6  interpolate       src/sampling.rs:7-24
+//   K7  modulate          src/modulation.rs:115-131
+//   K8  demod_hard        src/modulation.rs:33-56, :133-144
+//   K9  awgn_fill/apply   src/noise.rs:39-66    (Philox4x32-10 + Box-Muller, counter = sample index)
+//   K10 modem_fused       examples/modem.rs:15-32
+//   K11 expand / mseq     src/sequence.rs:18-53
+//   K13 bit-error / EVM partial sums
+// All float arithmetic that the reference's tests pin exactly uses the *_exact helpers
+// (no FMA contraction, IEEE division, denormals kept).
+#include "common.cuh"
+#include "internal.h"
+
+namespace ae {
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// =================================================================================================
+// K1 fused VecOps
+// =================================================================================================
+template <int W> struct VecIO;
+template <> struct VecIO<1> {
+  static __device__ __forceinline__ void load(float2 (&d)[1], const float2* p) { d[0] = ld_stream(p); }
+  static __device__ __forceinline__ void store(float2* p, const float2 (&d)[1]) { st_stream(p, d[0]); }
+};
+template <> struct VecIO<2> {
+  static __device__ __forceinline__ void load(float2 (&d)[2], const float2* p) {
+    const float4 v = ld_stream(reinterpret_cast<const float4*>(p));
+    d[0] = make_float2(v.x, v.y); d[1] = make_float2(v.z, v.w);
+  }
+  static __device__ __forceinline__ void store(float2* p, const float2 (&d)[2]) {
+    st_stream(reinterpret_cast<float4*>(p), make_float4(d[0].x, d[0].y, d[1].x, d[1].y));
+  }
+};
+
+template <int W>
+__device__ __forceinline__ void tape_apply(float2 (&x)[W], const TapeEntry& e, size_t idx) {
+  float2 o[W];
+  switch (e.op) {
+    case OP_SCALE:
+#pragma unroll
+      for (int w = 0; w < W; ++w) x[w] = cx_scale_exact(x[w], e.s);
+      break;
+    case OP_CONJ:
+#pragma unroll
+      for (int w = 0; w < W; ++w) x[w].y = -x[w].y;
+      break;
+    case OP_ZERO:
+#pragma unroll
+      for (int w = 0; w < W; ++w) x[w] = make_float2(0.0f, 0.0f);
+      break;
+    case OP_MIRROR: break;  // handled by the caller (register swap)
+    default:
+      VecIO<W>::load(o, e.operand + idx);
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        if (e.op == OP_MUL) x[w] = cx_mul_exact(x[w], o[w]);
+        else if (e.op == OP_DIV) x[w] = cx_div_exact(x[w], o[w]);
+        else if (e.op == OP_ADD) x[w] = cx_add_exact(x[w], o[w]);
+        else if (e.op == OP_SUB) x[w] = cx_sub_exact(x[w], o[w]);
+        else x[w] = o[w];  // OP_CLONE
+      }
+  }
+}
+
+constexpr int kVecThreads = 256;
+constexpr int kVecUnroll = 4;
+
+// no mirror in the tape: W consecutive samples per pack, kVecUnroll packs per thread
+template <int W>
+__global__ void __launch_bounds__(kVecThreads) vecops_kernel(float2* __restrict__ v, size_t n, const __grid_constant__ TapeParams p) {
+  const size_t packs = n / W;
+  const size_t base = (size_t)blockIdx.x * (kVecThreads * kVecUnroll) + threadIdx.x;
+  float2 x[kVecUnroll][W];
+#pragma unroll
+  for (int u = 0; u < kVecUnroll; ++u) {
+    const size_t i = base + (size_t)u * kVecThreads;
+    if (i < packs && p.load_self) VecIO<W>::load(x[u], v + i * W);
+    else {
+#pragma unroll
+      for (int w = 0; w < W; ++w) x[u][w] = make_float2(0.0f, 0.0f);
+    }
+  }
+  for (int k = 0; k < p.n_ops; ++k) {
+#pragma unroll
+    for (int u = 0; u < kVecUnroll; ++u) {
+      const size_t i = base + (size_t)u * kVecThreads;
+      if (i < packs) tape_apply<W>(x[u], p.e[k], i * W);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kVecUnroll; ++u) {
+    const size_t i = base + (size_t)u * kVecThreads;
+    if (i < packs) VecIO<W>::store(v + i * W, x[u]);
+  }
+  if (W == 2 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail element
+    float2 t[1];
+    const size_t i = n - 1;
+    t[0] = p.load_self ? v[i] : make_float2(0.0f, 0.0f);
+    for (int k = 0; k < p.n_ops; ++k) tape_apply<1>(t, p.e[k], i);
+    v[i] = t[0];
+  }
+}
+
+// tape contains vec_mirror: one thread owns the pair (p, p+mid) so the swap is a register
+// rename and operands are always read at the positions the data currently occupies.
+template <int W>
+__global__ void __launch_bounds__(kVecThreads) vecops_mirror_kernel(float2* __restrict__ v, size_t n, const __grid_constant__ TapeParams p) {
+  const size_t mid = n / 2;
+  const size_t packs = mid / W;  // host guarantees mid % W == 0
+  const size_t i = (size_t)blockIdx.x * kVecThreads + threadIdx.x;
+  if (i < packs) {
+    float2 lo[W], hi[W];
+    const size_t a = i * W, b = mid + i * W;
+    if (p.load_self) { VecIO<W>::load(lo, v + a); VecIO<W>::load(hi, v + b); }
+    else {
+#pragma unroll
+      for (int w = 0; w < W; ++w) { lo[w] = make_float2(0.0f, 0.0f); hi[w] = lo[w]; }
+    }
+    for (int k = 0; k < p.n_ops; ++k) {
+      if (p.e[k].op == OP_MIRROR) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) { const float2 t = lo[w]; lo[w] = hi[w]; hi[w] = t; }
+      } else {
+        tape_apply<W>(lo, p.e[k], a);
+        tape_apply<W>(hi, p.e[k], b);
+      }
+    }
+    VecIO<W>::store(v + a, lo);
+    VecIO<W>::store(v + b, hi);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd length: last element never moves (:157-161)
+    float2 t[1];
+    const size_t j = n - 1;
+    t[0] = p.load_self ? v[j] : make_float2(0.0f, 0.0f);
+    for (int k = 0; k < p.n_ops; ++k) tape_apply<1>(t, p.e[k], j);
+    v[j] = t[0];
+  }
+}
+
+void launch_vecops(float2* v, size_t n, const TapeParams& p, bool has_mirror, int, cudaStream_t st) {
+  if (n == 0) return;
+  bool aligned = ((uintptr_t)v % 16) == 0;
+  for (int k = 0; k < p.n_ops; ++k)
+    if (p.e[k].operand && ((uintptr_t)p.e[k].operand % 16) != 0) aligned = false;
+  if (!has_mirror) {
+    if (aligned && n >= 2) {
+      vecops_kernel<2><<<cdiv(n / 2, kVecThreads * kVecUnroll), kVecThreads, 0, st>>>(v, n, p);
+    } else {
+      vecops_kernel<1><<<cdiv(n, kVecThreads * kVecUnroll), kVecThreads, 0, st>>>(v, n, p);
+    }
+  } else {
+    const size_t mid = n / 2;
+    if (aligned && (mid % 2) == 0 && mid >= 2) {
+      vecops_mirror_kernel<2><<<cdiv(mid / 2, kVecThreads), kVecThreads, 0, st>>>(v, n, p);
+    } else {
+      vecops_mirror_kernel<1><<<cdiv(mid ? mid : 1, kVecThreads), kVecThreads, 0, st>>>(v, n, p);
+    }
+  }
+}
+
+// =================================================================================================
+// K5 downsample (src/sampling.rs:38-41): dst[i] = src[i*dec]
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) downsample_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t n_dst, size_t dec) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n_dst) dst[i] = src[i * dec];
+}
+// dec == 2 / 4 with 16-byte aligned cf32: each thread reads whole 16-byte vectors of the source
+// it needs and writes one float4 (two outputs) so every store instruction is a full 512-byte row.
+template <int DEC>
+__global__ void __launch_bounds__(256) downsample_cf32_vec_kernel(const float2* __restrict__ src, float2* __restrict__ dst, size_t n_pairs) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n_pairs) {
+    const float2 a = __ldcs(src + (2 * i) * DEC);
+    const float2 b = __ldcs(src + (2 * i + 1) * DEC);
+    __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(a.x, a.y, b.x, b.y));
+  }
+}
+void launch_downsample_cf32(const float2* src, float2* dst, size_t n_dst, size_t dec, cudaStream_t st) {
+  if (n_dst == 0) return;
+  const bool al = ((uintptr_t)dst % 16) == 0;
+  const size_t pairs = n_dst / 2;
+  if (al && pairs && (dec == 4 || dec == 2)) {
+    if (dec == 4) downsample_cf32_vec_kernel<4><<<cdiv(pairs, 256), 256, 0, st>>>(src, dst, pairs);
+    else downsample_cf32_vec_kernel<2><<<cdiv(pairs, 256), 256, 0, st>>>(src, dst, pairs);
+    if (n_dst & 1) downsample_kernel<float2><<<1, 256, 0, st>>>(src + (n_dst - 1) * dec, dst + (n_dst - 1), 1, dec);
+  } else {
+    downsample_kernel<float2><<<cdiv(n_dst, 256), 256, 0, st>>>(src, dst, n_dst, dec);
+  }
+}
+void launch_downsample_u8(const uint8_t* src, uint8_t* dst, size_t n_dst, size_t dec, cudaStream_t st) {
+  if (n_dst == 0) return;
+  downsample_kernel<uint8_t><<<cdiv(n_dst, 256), 256, 0, st>>>(src, dst, n_dst, dec);
+}
+
+// =================================================================================================
+// K6 interpolate (src/sampling.rs:7-24).  One thread per input window; K1 = n_between+1 outputs.
+//   rate = ((x2.re-x1.re)/K1, (x2.im-x1.im)/K1);  out = (x1.re + i*rate.0, x1.{re|im} + i*rate.1)
+// =================================================================================================
+template <int K1T>  // 0 = runtime K1
+__global__ void __launch_bounds__(256) interpolate_kernel(const float2* __restrict__ src, size_t n_src, float2* __restrict__ dst,
+                                                          int k1_rt, int compat, int vec_ok) {
+  const int K1 = K1T ? K1T : k1_rt;
+  const size_t w = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (w + 1 < n_src) {
+    const float2 x1 = __ldg(src + w), x2 = __ldg(src + w + 1);
+    const float div = (float)K1;
+    const float r0 = __fdiv_rn(__fsub_rn(x2.x, x1.x), div);
+    const float r1 = __fdiv_rn(__fsub_rn(x2.y, x1.y), div);
+    const float imb = compat == AE_COMPAT_REFERENCE ? x1.x : x1.y;  // :19 uses x1.re
+    float2* o = dst + w * (size_t)K1;
+    if (K1T > 0 && (K1T % 2) == 0 && vec_ok) {
+#pragma unroll
+      for (int i = 0; i < K1T; i += 2) {
+        const float f0 = (float)i, f1 = (float)(i + 1);
+        const float4 v = make_float4(__fadd_rn(x1.x, __fmul_rn(f0, r0)), __fadd_rn(imb, __fmul_rn(f0, r1)),
+                                     __fadd_rn(x1.x, __fmul_rn(f1, r0)), __fadd_rn(imb, __fmul_rn(f1, r1)));
+        __stcs(reinterpret_cast<float4*>(o + i), v);
+      }
+    } else {
+      for (int i = 0; i < K1; ++i) {
+        const float f = (float)i;
+        __stcs(o + i, make_float2(__fadd_rn(x1.x, __fmul_rn(f, r0)), __fadd_rn(imb, __fmul_rn(f, r1))));
+      }
+    }
+  } else if (w + 1 == n_src) {
+    dst[w * (size_t)K1] = src[w];  // dst.push(*src.last().unwrap()) :23
+  }
+}
+void launch_interpolate(const float2* src, size_t n_src, float2* dst, size_t n_between, int compat, cudaStream_t st) {
+  if (n_src == 0) return;
+  const int k1 = (int)(n_between + 1);
+  const int vec_ok = ((uintptr_t)dst % 16) == 0;
+  const unsigned g = cdiv(n_src, 256);
+  if (k1 == 4) interpolate_kernel<4><<<g, 256, 0, st>>>(src, n_src, dst, k1, compat, vec_ok);
+  else if (k1 == 2) interpolate_kernel<2><<<g, 256, 0, st>>>(src, n_src, dst, k1, compat, vec_ok);
+  else if (k1 == 8) interpolate_kernel<8><<<g, 256, 0, st>>>(src, n_src, dst, k1, compat, vec_ok);
+  else interpolate_kernel<0><<<g, 256, 0, st>>>(src, n_src, dst, k1, compat, 0);
+}
+
+// =================================================================================================
+// K7 modulate (src/modulation.rs:115-121): chunks(BPS) -> index -> LUT
+// =================================================================================================
+template <int BPS>
+__device__ __forceinline__ float2 mod_symbol(const ModTable& tab, const uint8_t* b, int* errflag) {
+  unsigned idx;
+  if (BPS == 1) idx = b[0];                                                 // :10
+  else idx = (uint8_t)((uint8_t)(b[1] << 1) + b[0]);                        // :24 (u8 arithmetic)
+  if (idx >= (unsigned)tab.len) { atomicOr(errflag, DEVERR_MOD_INDEX); return make_float2(0.0f, 0.0f); }
+  return tab.t[idx];
+}
+template <int BPS>
+__global__ void __launch_bounds__(256) modulate_kernel(const __grid_constant__ ModTable tab, const uint8_t* __restrict__ bits,
+                                                       float2* __restrict__ out, size_t n_out, int vec_ok, int* errflag) {
+  const size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;  // group of 4 symbols
+  const size_t s0 = g * 4;
+  if (s0 >= n_out) return;
+  if (vec_ok && s0 + 4 <= n_out) {
+    uint8_t b[4 * BPS];
+    if (BPS == 2) *reinterpret_cast<uint2*>(b) = __ldcs(reinterpret_cast<const uint2*>(bits + s0 * 2));
+    else *reinterpret_cast<uint32_t*>(b) = __ldcs(reinterpret_cast<const uint32_t*>(bits + s0));
+    float2 s[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] = mod_symbol<BPS>(tab, b + i * BPS, errflag);
+    float4* o = reinterpret_cast<float4*>(out + s0);
+    __stcs(o, make_float4(s[0].x, s[0].y, s[1].x, s[1].y));
+    __stcs(o + 1, make_float4(s[2].x, s[2].y, s[3].x, s[3].y));
+  } else {
+    for (size_t s = s0; s < n_out && s < s0 + 4; ++s) out[s] = mod_symbol<BPS>(tab, bits + s * BPS, errflag);
+  }
+}
+void launch_modulate(const ModTable& tab, const uint8_t* bits, size_t, float2* out, size_t n_out, int* errflag, cudaStream_t st) {
+  if (n_out == 0) return;
+  const int vec_ok = ((uintptr_t)bits % 8) == 0 && ((uintptr_t)out % 16) == 0;
+  const unsigned g = cdiv(cdiv(n_out, 4), 256);
+  if (tab.len == 2) modulate_kernel<1><<<g, 256, 0, st>>>(tab, bits, out, n_out, vec_ok, errflag);
+  else modulate_kernel<2><<<g, 256, 0, st>>>(tab, bits, out, n_out, vec_ok, errflag);
+}
+
+// =================================================================================================
+// K8 hard demod.  BPSK: generic default impl (:133-144); QPSK: the override (:33-56) which emits
+// idx&1 then idx&2 in {0,2}; compat=corrected emits (idx>>1)&1.
+// =================================================================================================
+template <int M>
+__device__ __forceinline__ void demod_emit(float2 s, const float2 (&tab)[M], int compat, uint8_t* o) {
+  const unsigned idx = demod_index<M>(s, tab);
+  o[0] = (uint8_t)(idx & 1u);
+  if (M == 4) o[1] = compat == AE_COMPAT_REFERENCE ? (uint8_t)(idx & 2u) : (uint8_t)((idx >> 1) & 1u);
+}
+template <int M>
+__global__ void __launch_bounds__(256) demod_kernel(const __grid_constant__ ModTable tabp, const float2* __restrict__ sym, size_t n,
+                                                    uint8_t* __restrict__ bits, int compat, int vec_ok) {
+  constexpr int BPS = M == 2 ? 1 : 2;
+  float2 tab[M];
+#pragma unroll
+  for (int c = 0; c < M; ++c) tab[c] = tabp.t[c];
+  const size_t s0 = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (s0 >= n) return;
+  if (vec_ok && s0 + 4 <= n) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(sym + s0));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(sym + s0) + 1);
+    uint8_t o[4 * BPS];
+    demod_emit<M>(make_float2(a.x, a.y), tab, compat, o);
+    demod_emit<M>(make_float2(a.z, a.w), tab, compat, o + BPS);
+    demod_emit<M>(make_float2(b.x, b.y), tab, compat, o + 2 * BPS);
+    demod_emit<M>(make_float2(b.z, b.w), tab, compat, o + 3 * BPS);
+    if (BPS == 2) __stcs(reinterpret_cast<uint2*>(bits + s0 * 2), *reinterpret_cast<uint2*>(o));
+    else __stcs(reinterpret_cast<uint32_t*>(bits + s0), *reinterpret_cast<uint32_t*>(o));
+  } else {
+    for (size_t s = s0; s < n && s < s0 + 4; ++s) demod_emit<M>(sym[s], tab, compat, bits + s * BPS);
+  }
+}
+void launch_demod(const ModTable& tab, const float2* sym, size_t n, uint8_t* bits, int compat, cudaStream_t st) {
+  if (n == 0) return;
+  const int vec_ok = ((uintptr_t)sym % 16) == 0 && ((uintptr_t)bits % 8) == 0;
+  const unsigned g = cdiv(cdiv(n, 4), 256);
+  if (tab.len == 2) demod_kernel<2><<<g, 256, 0, st>>>(tab, sym, n, bits, compat, vec_ok);
+  else demod_kernel<4><<<g, 256, 0, st>>>(tab, sym, n, bits, compat, vec_ok);
+}
+
+// =================================================================================================
+// K9 AWGN (src/noise.rs:39-66).  Thread = one Philox block = the sample pair (2P, 2P+1) of the
+// stream; results depend only on (seed, stream, global sample index), never on the grid shape.
+// =================================================================================================
+template <bool APPLY>
+__global__ void __launch_bounds__(256) awgn_kernel(float2* __restrict__ buf, size_t n, float scale, int twice, uint64_t seed,
+                                                   uint64_t stream, uint64_t offset, int vec_ok) {
+  const uint64_t p0 = offset >> 1;
+  const uint64_t P = p0 + (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const uint64_t g0 = 2 * P, g1 = g0 + 1;
+  if (g0 >= offset + n) return;
+  float2 z0, z1;
+  awgn_unit_pair(seed, stream, P, z0, z1);
+  // next(): (N(0,1) as f32) * scale (:41-42); apply(): ... .scale(sc) once more (:58)
+  z0 = cx_scale_exact(z0, scale); z1 = cx_scale_exact(z1, scale);
+  if (twice) { z0 = cx_scale_exact(z0, scale); z1 = cx_scale_exact(z1, scale); }
+  const bool in0 = g0 >= offset, in1 = g1 < offset + n;
+  if (vec_ok && in0 && in1) {
+    float4* q = reinterpret_cast<float4*>(buf + (g0 - offset));
+    if (APPLY) {
+      const float4 s = __ldcs(q);
+      __stcs(q, make_float4(__fadd_rn(s.x, z0.x), __fadd_rn(s.y, z0.y), __fadd_rn(s.z, z1.x), __fadd_rn(s.w, z1.y)));
+    } else {
+      __stcs(q, make_float4(z0.x, z0.y, z1.x, z1.y));
+    }
+  } else {
+    if (in0) { float2* q = buf + (g0 - offset); *q = APPLY ? cx_add_exact(*q, z0) : z0; }
+    if (in1) { float2* q = buf + (g1 - offset); *q = APPLY ? cx_add_exact(*q, z1) : z1; }
+  }
+}
+static void awgn_launch(bool apply, float2* buf, size_t n, float scale, int twice, uint64_t seed, uint64_t stream,
+                        uint64_t offset, cudaStream_t st) {
+  if (n == 0) return;
+  const uint64_t pairs = ((offset + n + 1) >> 1) - (offset >> 1);
+  const int vec_ok = ((offset & 1) == 0) && ((uintptr_t)buf % 16) == 0;
+  const unsigned g = cdiv(pairs, 256);
+  if (apply) awgn_kernel<true><<<g, 256, 0, st>>>(buf, n, scale, twice, seed, stream, offset, vec_ok);
+  else awgn_kernel<false><<<g, 256, 0, st>>>(buf, n, scale, twice, seed, stream, offset, vec_ok);
+}
+void launch_awgn_fill(float2* dst, size_t n, float scale, uint64_t seed, uint64_t stream, uint64_t offset, cudaStream_t st) {
+  awgn_launch(false, dst, n, scale, 0, seed, stream, offset, st);
+}
+void launch_awgn_apply(float2* sig, size_t n, float scale, int twice, uint64_t seed, uint64_t stream, uint64_t offset,
+                       cudaStream_t st) {
+  awgn_launch(true, sig, n, scale, twice, seed, stream, offset, st);
+}
+
+// =================================================================================================
+// warp / block reductions for the statistics
+// =================================================================================================
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// =================================================================================================
+// K10 modem_fused (examples/modem.rs:15-32): modulate -> Awgn::apply -> demod_naive (+ bit errors)
+// in registers.  4 B/symbol of HBM traffic for QPSK: 2 B bits in + 2 B bits out.
+// Thread = 4 symbols (two Philox blocks).
+// =================================================================================================
+template <int M>
+__global__ void __launch_bounds__(256) modem_kernel(const __grid_constant__ ModTable tabp, const uint8_t* __restrict__ bin, size_t nsym,
+                                                    uint8_t* __restrict__ bout, float scale, int twice, uint64_t seed, uint64_t stream,
+                                                    uint64_t offset, int compat, ae_stats* stats, int* errflag, int vec_ok) {
+  constexpr int BPS = M == 2 ? 1 : 2;
+  float2 tab[M];
+#pragma unroll
+  for (int c = 0; c < M; ++c) tab[c] = tabp.t[c];
+  unsigned long long errs = 0;
+  // pairs are aligned to the GLOBAL sample index so the stream does not depend on `offset` parity
+  const uint64_t p0 = offset >> 1;
+  const uint64_t npairs = ((offset + nsym + 1) >> 1) - p0;
+  for (uint64_t q = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 2; q < npairs; q += (uint64_t)gridDim.x * 512) {
+    uint8_t bi[4 * BPS], bo[4 * BPS];
+    const uint64_t g0 = 2 * (p0 + q);           // global index of the first of 4 samples
+    const long long l0 = (long long)(g0 - offset);  // local symbol index (may be -1)
+    const bool full = vec_ok && l0 >= 0 && (size_t)(l0 + 4) <= nsym;
+    if (full) {
+      if (BPS == 2) *reinterpret_cast<uint2*>(bi) = __ldcs(reinterpret_cast<const uint2*>(bin + l0 * 2));
+      else *reinterpret_cast<uint32_t*>(bi) = __ldcs(reinterpret_cast<const uint32_t*>(bin + l0));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long l = l0 + i;
+        const bool ok = l >= 0 && (size_t)l < nsym;
+#pragma unroll
+        for (int b = 0; b < BPS; ++b) bi[i * BPS + b] = ok ? bin[l * BPS + b] : 0;
+      }
+    }
+    float2 z[4];
+    awgn_unit_pair(seed, stream, p0 + q, z[0], z[1]);
+    awgn_unit_pair(seed, stream, p0 + q + 1, z[2], z[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long l = l0 + i;
+      const bool ok = l >= 0 && (size_t)l < nsym;
+      unsigned idx;
+      if (BPS == 1) idx = bi[i];
+      else idx = (uint8_t)((uint8_t)(bi[2 * i + 1] << 1) + bi[2 * i]);
+      float2 s = make_float2(0.0f, 0.0f);
+      if (idx < (unsigned)M) s = tab[idx];
+      else if (ok) atomicOr(errflag, DEVERR_MOD_INDEX);
+      float2 nz = cx_scale_exact(z[i], scale);
+      if (twice) nz = cx_scale_exact(nz, scale);
+      s = cx_add_exact(s, nz);
+      demod_emit<M>(s, tab, compat, bo + i * BPS);
+      if (ok) {
+#pragma unroll
+        for (int b = 0; b < BPS; ++b) errs += ((bi[i * BPS + b] != 0) != (bo[i * BPS + b] != 0));
+      }
+    }
+    if (full) {
+      if (BPS == 2) __stcs(reinterpret_cast<uint2*>(bout + l0 * 2), *reinterpret_cast<uint2*>(bo));
+      else __stcs(reinterpret_cast<uint32_t*>(bout + l0), *reinterpret_cast<uint32_t*>(bo));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long l = l0 + i;
+        if (l >= 0 && (size_t)l < nsym) {
+#pragma unroll
+          for (int b = 0; b < BPS; ++b) bout[l * BPS + b] = bo[i * BPS + b];
+        }
+      }
+    }
+  }
+  if (stats) {
+    errs = warp_sum_u64(errs);
+    if ((threadIdx.x & 31) == 0 && errs) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->bit_errors), errs);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_bits), (unsigned long long)nsym * BPS);
+  }
+}
+void launch_modem_fused(const ModTable& tab, const uint8_t* bits_in, size_t nbits, uint8_t* bits_out, float scale, int twice,
+                        uint64_t seed, uint64_t stream, uint64_t offset, int compat, ae_stats* stats, int* errflag,
+                        int sm_count, cudaStream_t st) {
+  const int bps = tab.len == 2 ? 1 : 2;
+  const size_t nsym = nbits / bps;
+  if (nsym == 0) return;
+  const int vec_ok = ((uintptr_t)bits_in % 8) == 0 && ((uintptr_t)bits_out % 8) == 0 && (offset % 2) == 0;
+  const uint64_t npairs = ((offset + nsym + 1) >> 1) - (offset >> 1);
+  unsigned g = cdiv(cdiv(npairs, 2), 256);
+  const unsigned cap = (unsigned)sm_count * 16;
+  if (g > cap) g = cap;
+  if (tab.len == 2)
+    modem_kernel<2><<<g, 256, 0, st>>>(tab, bits_in, nsym, bits_out, scale, twice, seed, stream, offset, compat, stats, errflag, vec_ok);
+  else
+    modem_kernel<4><<<g, 256, 0, st>>>(tab, bits_in, nsym, bits_out, scale, twice, seed, stream, offset, compat, stats, errflag, vec_ok);
+}
+
+// =================================================================================================
+// K11 sequence
+// =================================================================================================
+__global__ void expand_kernel(uint64_t seed, size_t len, uint8_t* out) {  // src/sequence.rs:18-21
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < len) out[i] = (uint8_t)((seed >> i) & 1u);
+}
+void launch_expand(uint64_t seed, size_t len, uint8_t* out, cudaStream_t st) {
+  if (len) expand_kernel<<<cdiv(len, 256), 256, 0, st>>>(seed, len, out);
+}
+
+// GF(2)[z] arithmetic modulo p(z) = z^deg + poly_low(z), deg <= 64
+__device__ __forceinline__ uint64_t gf2_mulmod(uint64_t a, uint64_t b, uint64_t poly_low, int deg) {
+  // shift-and-add with reduction folded into every doubling of `a`
+  uint64_t r = 0;
+  const uint64_t top = 1ull << (deg - 1);
+  for (int i = 0; i < deg; ++i) {
+    if ((b >> i) & 1ull) r ^= a;
+    const bool carry = (a & top) != 0;
+    a = (deg == 64) ? (a << 1) : ((a << 1) & ((1ull << deg) - 1ull));
+    if (carry) a ^= poly_low;
+  }
+  return r;
+}
+constexpr int kMseqBitsPerThread = 256;
+constexpr int kMseqThreads = 128;
+// out[i] = x[i], i < len, where x obeys x[n] = parity(window & poly_low) with window bit j = x[n-deg+j]
+// and x[0..deg) = state bits.  Jump-ahead: z^n mod p(z) = sum c_i z^i  =>  x[n] = parity(c & state).
+__global__ void __launch_bounds__(kMseqThreads) mseq_kernel(uint64_t state, uint64_t poly_low, int deg, size_t len, uint8_t* __restrict__ out) {
+  __shared__ uint64_t s_block;
+  const size_t block_start = (size_t)blockIdx.x * kMseqThreads * kMseqBitsPerThread;
+  if (threadIdx.x == 0) {
+    // z^block_start mod p by square-and-multiply
+    uint64_t r = 1ull, sq = (deg == 1) ? poly_low : 2ull;  // z mod p
+    size_t e = block_start;
+    while (e) {
+      if (e & 1) r = gf2_mulmod(r, sq, poly_low, deg);
+      sq = gf2_mulmod(sq, sq, poly_low, deg);
+      e >>= 1;
+    }
+    s_block = r;
+  }
+  __syncthreads();
+  const size_t n0 = block_start + (size_t)threadIdx.x * kMseqBitsPerThread;
+  if (n0 >= len) return;
+  // z^(256 t) mod p
+  uint64_t r = 1ull, sq = (deg == 1) ? poly_low : 2ull;
+  unsigned e = threadIdx.x * kMseqBitsPerThread;
+  while (e) {
+    if (e & 1) r = gf2_mulmod(r, sq, poly_low, deg);
+    sq = gf2_mulmod(sq, sq, poly_low, deg);
+    e >>= 1;
+  }
+  r = gf2_mulmod(r, s_block, poly_low, deg);
+  // first deg bits of this thread's run via successive multiplication by z
+  const uint64_t top = 1ull << (deg - 1);
+  uint64_t window = 0;
+  for (int j = 0; j < deg; ++j) {
+    window |= (uint64_t)(__popcll(r & state) & 1) << j;
+    const bool carry = (r & top) != 0;
+    r = (deg == 64) ? (r << 1) : ((r << 1) & ((1ull << deg) - 1ull));
+    if (carry) r ^= poly_low;
+  }
+  // emit: bits [n0, n0+256); window holds x[n .. n+deg) for the current n
+  size_t n = n0;
+  const size_t end = (n0 + kMseqBitsPerThread < len) ? n0 + kMseqBitsPerThread : len;
+  while (n < end) {
+    const uint8_t bit = (uint8_t)(window & 1ull);
+    out[n++] = bit;
+    const uint64_t nb = (uint64_t)(__popcll(window & poly_low) & 1);
+    window = (window >> 1) | (nb << (deg - 1));
+  }
+}
+void launch_mseq(uint64_t state, uint64_t poly_low, int deg, size_t len, uint8_t* out, cudaStream_t st) {
+  if (len == 0) return;
+  mseq_kernel<<<cdiv(len, (size_t)kMseqThreads * kMseqBitsPerThread), kMseqThreads, 0, st>>>(state, poly_low, deg, len, out);
+}
+
+// =================================================================================================
+// K13 statistics partial sums (the operands of the only cross-GPU reduction)
+// =================================================================================================
+__global__ void __launch_bounds__(256) bit_errors_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n,
+                                                         ae_stats* stats, int vec_ok) {
+  unsigned long long errs = 0;
+  const size_t tid = (size_t)blockIdx.x * 256 + threadIdx.x, nth = (size_t)gridDim.x * 256;
+  size_t done = 0;
+  if (vec_ok) {
+    const size_t nv = n / 16;
+    const uint4* a4 = reinterpret_cast<const uint4*>(a);
+    const uint4* b4 = reinterpret_cast<const uint4*>(b);
+    for (size_t i = tid; i < nv; i += nth) {
+      const uint4 x = __ldcs(a4 + i), y = __ldcs(b4 + i);
+      errs += __popc(__vcmpne4(x.x, 0) ^ __vcmpne4(y.x, 0)) + __popc(__vcmpne4(x.y, 0) ^ __vcmpne4(y.y, 0)) +
+              __popc(__vcmpne4(x.z, 0) ^ __vcmpne4(y.z, 0)) + __popc(__vcmpne4(x.w, 0) ^ __vcmpne4(y.w, 0));
+    }
+    errs >>= 3;  // 8 mask bits per differing byte
+    done = nv * 16;
+  }
+  for (size_t i = done + tid; i < n; i += nth) errs += ((a[i] != 0) != (b[i] != 0));
+  errs = warp_sum_u64(errs);
+  if ((threadIdx.x & 31) == 0 && errs) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->bit_errors), errs);
+  if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_bits), (unsigned long long)n);
+}
+void launch_bit_errors(const uint8_t* a, const uint8_t* b, size_t n, ae_stats* stats, int sm_count, cudaStream_t st) {
+  if (n == 0) return;
+  const int vec_ok = ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0;
+  unsigned g = cdiv(cdiv(n, 16), 256);
+  const unsigned cap = (unsigned)sm_count * 8;
+  if (g > cap) g = cap;
+  bit_errors_kernel<<<g, 256, 0, st>>>(a, b, n, stats, vec_ok);
+}
+__global__ void __launch_bounds__(256) evm_acc_kernel(const float2* __restrict__ act, const float2* __restrict__ ref, size_t n, ae_stats* stats) {
+  double e = 0.0, r = 0.0;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const float2 a = __ldcs(act + i), b = __ldcs(ref + i);
+    const float dr = a.x - b.x, di = a.y - b.y;
+    e += (double)(dr * dr + di * di);
+    r += (double)(b.x * b.x + b.y * b.y);
+  }
+  e = warp_sum_f64(e); r = warp_sum_f64(r);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&stats->err_pow, e); atomicAdd(&stats->ref_pow, r); }
+}
+void launch_evm_acc(const float2* act, const float2* ref, size_t n, ae_stats* stats, int sm_count, cudaStream_t st) {
+  if (n == 0) return;
+  unsigned g = cdiv(n, 256 * 4);
+  const unsigned cap = (unsigned)sm_count * 8;
+  if (g > cap) g = cap;
+  evm_acc_kernel<<<g, 256, 0, st>>>(act, ref, n, stats);
+}
+
+}  // namespace ae

@@ -1,0 +1,138 @@
+// fft.cu — K2 batched power-of-two FFT and K2b any-length fallback (sm_100a).
+// Replaces rustfft under fft::Cfft (src/fft.rs:134-235).  Scale::{SN,N,X} (src/fft.rs:22-37) is
+// folded into the last pass as one separately rounded multiply, which reproduces the
+// reference's "transform, then vec_scale" rounding sequence on this kernel's own output.
+#include "fft_device.cuh"
+#include "internal.h"
+
+namespace ae {
+
+// -------------------------------------------------------------------------------------------------
+// power-of-two kernel: F frames per CTA, T = N/16 threads per frame, algorithmic traffic
+// 16 B/sample (8 read + 8 written), 5*N*log2(N) flop per frame.
+// -------------------------------------------------------------------------------------------------
+template <int N>
+struct FftLaunch {
+  static constexpr int T = FftCfg<N>::T;
+  // frames per CTA: 256-thread CTAs (named barriers allow <= 15 frame slots when T >= 32)
+  static constexpr int F = T >= 256 ? 1 : (256 / T);
+  static constexpr int THREADS = F * T;
+  static constexpr size_t SMEM = (size_t)F * FftCfg<N>::SMEM_ELEMS * sizeof(float2);
+};
+
+template <int N, bool INV>
+__global__ void __launch_bounds__(FftLaunch<N>::THREADS)
+fft_pow2_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ tw, size_t frames,
+                float scale, int do_scale) {
+  using C = FftCfg<N>;
+  using LC = FftLaunch<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  const int f = threadIdx.x / C::T;
+  const int t = threadIdx.x % C::T;
+  const size_t frame = (size_t)blockIdx.x * LC::F + f;
+  if (frame >= frames) return;  // whole frame groups leave together (barriers are per frame)
+  const float2* src = in + frame * N;
+  float2 x[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) x[m] = ld_stream(src + t + m * C::T);
+  fft_frame<N, INV>(x, smem + f * C::SMEM_ELEMS, tw, t, f);
+  float2* dst = out + frame * N;
+  if (do_scale) {
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[m] = cx_scale_exact(x[m], scale);
+  }
+#pragma unroll
+  for (int m = 0; m < 16; ++m) st_stream(dst + t + m * C::T, x[m]);
+}
+
+template <int N>
+static void launch_pow2_n(const float2* in, float2* out, size_t frames, const float2* tw, bool inverse, bool do_scale,
+                          float scale, cudaStream_t st) {
+  using LC = FftLaunch<N>;
+  const unsigned grid = (unsigned)((frames + LC::F - 1) / LC::F);
+  if (inverse) {
+    if (LC::SMEM > 48 * 1024)
+      cudaFuncSetAttribute(fft_pow2_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
+    fft_pow2_kernel<N, true><<<grid, LC::THREADS, LC::SMEM, st>>>(in, out, tw, frames, scale, do_scale);
+  } else {
+    if (LC::SMEM > 48 * 1024)
+      cudaFuncSetAttribute(fft_pow2_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
+    fft_pow2_kernel<N, false><<<grid, LC::THREADS, LC::SMEM, st>>>(in, out, tw, frames, scale, do_scale);
+  }
+}
+
+bool fft_pow2_supported(size_t n) { return n >= 16 && n <= 16384 && (n & (n - 1)) == 0; }
+
+void launch_fft_pow2(const float2* in, float2* out, size_t n, size_t frames, const float2* tw, bool inverse, bool do_scale,
+                     float scale, cudaStream_t st) {
+  if (frames == 0) return;
+  switch (n) {
+#define AE_CASE(NN) case NN: launch_pow2_n<NN>(in, out, frames, tw, inverse, do_scale, scale, st); break;
+    AE_CASE(16) AE_CASE(32) AE_CASE(64) AE_CASE(128) AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048)
+    AE_CASE(4096) AE_CASE(8192) AE_CASE(16384)
+#undef AE_CASE
+    default: break;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K2b any-length fallback (Cfft::with_len accepts any len; N = 100 is a reference test,
+// src/vecops.rs:445-463).  One global-memory Stockham pass per factor p of N; each thread produces
+// ONE output  out[(j-k)*p + k + q*NS] = sum_r in[j + r*N/p] * W_N^( r*k*N/(NS*p) + ((r*q) mod p)*N/p ).
+// Correctness-first: O(N * sum(p)) work, f32 accumulation.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fft_generic_pass_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                               const float2* __restrict__ tw, unsigned n, unsigned p, unsigned ns,
+                                                               int inverse, int do_scale, float scale) {
+  const unsigned o = blockIdx.x * 256 + threadIdx.x;  // output slot: (j, q)
+  if (o >= n) return;
+  const size_t frame = blockIdx.y;
+  const unsigned m = n / p;       // butterflies
+  const unsigned j = o % m, q = o / m;
+  const unsigned k = j % ns;
+  const unsigned tws = n / (ns * p), wp = n / p;
+  const float2* src = in + frame * n;
+  float2 acc = make_float2(0.0f, 0.0f);
+  for (unsigned r = 0; r < p; ++r) {
+    const unsigned long long e = (unsigned long long)r * k * tws + (unsigned long long)((r * (unsigned long long)q) % p) * wp;
+    float2 w = __ldg(tw + (unsigned)(e % n));
+    if (inverse) w.y = -w.y;
+    cx_fma(acc, src[j + r * m], w);
+  }
+  if (do_scale) acc = cx_scale_exact(acc, scale);
+  out[frame * n + (size_t)(j - k) * p + k + (size_t)q * ns] = acc;
+}
+
+void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n, size_t frames, const float2* tw,
+                        const uint32_t* radices, int n_radices, bool inverse, bool do_scale, float scale, cudaStream_t st) {
+  if (frames == 0 || n == 0) return;
+  // scratch holds 2*n*frames cf32: ping-pong halves; the last pass writes `out`
+  constexpr size_t kMaxY = 32768;  // gridDim.y limit is 65535
+  for (size_t f0 = 0; f0 < frames; f0 += kMaxY) {
+    const size_t fc = frames - f0 < kMaxY ? frames - f0 : kMaxY;
+    float2* bufs[2] = {scratch + f0 * n, scratch + n * frames + f0 * n};
+    const float2* cur = in + f0 * n;
+    float2* o = out + f0 * n;
+    const dim3 grid((unsigned)((n + 255) / 256), (unsigned)fc);
+    if (n == 1 || n_radices <= 1) {
+      // single pass: never read and write the same buffer
+      if (cur == o) {
+        cudaMemcpyAsync(bufs[0], cur, fc * n * sizeof(float2), cudaMemcpyDeviceToDevice, st);
+        cur = bufs[0];
+      }
+      fft_generic_pass_kernel<<<grid, 256, 0, st>>>(cur, o, tw, (unsigned)n, (unsigned)n, 1, inverse, do_scale, scale);
+      continue;
+    }
+    unsigned ns = 1;
+    for (int i = 0; i < n_radices; ++i) {
+      const bool last = (i == n_radices - 1);
+      float2* dst = last ? o : bufs[i & 1];
+      fft_generic_pass_kernel<<<grid, 256, 0, st>>>(cur, dst, tw, (unsigned)n, radices[i], ns, inverse, last && do_scale, scale);
+      cur = dst;
+      ns *= radices[i];
+    }
+  }
+}
+
+}  // namespace ae

@@ -1,0 +1,183 @@
+// fir.cu — K3 direct-form FIR and K4 overlap-save FIR (sm_100a).
+//
+// The reference's src/fir.rs:1-22 is a constructor-only stub; the filter is the
+// textbook definition  y[n] = sum_{k<T} h[k] x[n-k],  output length = input length, with either
+// a carried history of T-1 samples (streaming) or zero state at the start of every frame.
+// Parity tier T1: EVM against the f64 direct form (oracle/aether_oracle.cpp ora_fir_f64).
+#include "fft_device.cuh"
+#include "internal.h"
+
+namespace ae {
+
+// -------------------------------------------------------------------------------------------------
+// K3 direct form.  FP32-bound: 4 FFMA per tap per output (8*T flop/sample) against 16 B/sample.
+// Each thread owns S = 8 consecutive outputs and slides an 8-register window over the input
+// (one new cf32 from shared memory per tap), so the inner loop is 32 FFMA : 2 LDS.
+// The tap loop is unrolled by 8 so the window rotation is pure register renaming.
+// -------------------------------------------------------------------------------------------------
+constexpr int kFirS = 8;
+constexpr int kFirThreads = 256;
+constexpr int kFirTile = kFirS * kFirThreads;  // 2048 outputs per CTA
+
+__device__ __forceinline__ int fir_pad(int i) { return i + (i >> 3); }
+
+__global__ void __launch_bounds__(kFirThreads)
+fir_direct_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_t n, const float2* __restrict__ taps, int tp,
+                  const float2* __restrict__ history, size_t frame_len) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* hs = reinterpret_cast<float2*>(smem_raw);  // tp taps
+  float2* xs = hs + tp;                              // padded tile: kFirTile + tp inputs
+  const long long tile0 = (long long)blockIdx.x * kFirTile;
+  const int n_in = kFirTile + tp;
+  for (int i = threadIdx.x; i < tp; i += kFirThreads) hs[i] = __ldg(taps + i);
+  // tile element i <-> global sample g = tile0 - tp + i
+  for (int i = threadIdx.x; i < n_in; i += kFirThreads) {
+    const long long g = tile0 - tp + i;
+    float2 v = make_float2(0.0f, 0.0f);
+    if (g >= 0) { if ((size_t)g < n) v = ld_stream(x + g); }
+    else if (history && g >= -(long long)(tp - 1)) v = __ldg(history + (tp - 1) + g);
+    xs[fir_pad(i)] = v;
+  }
+  __syncthreads();
+  const long long n0 = tile0 + (long long)threadIdx.x * kFirS;
+  if ((size_t)n0 >= n) return;
+  // first sample of this thread's frame (frame_len % 8 == 0 guaranteed by the host)
+  const long long fstart = frame_len ? (n0 / (long long)frame_len) * (long long)frame_len : -(1ll << 62);
+  const int base = tp + threadIdx.x * kFirS;  // tile index of x[n0]
+  float2 acc[kFirS], w[kFirS];
+#pragma unroll
+  for (int s = 0; s < kFirS; ++s) {
+    acc[s] = make_float2(0.0f, 0.0f);
+    w[s] = xs[fir_pad(base + s)];  // x[n0+s] belongs to the frame by construction
+  }
+  for (int kb = 0; kb < tp; kb += kFirS) {
+#pragma unroll
+    for (int kk = 0; kk < kFirS; ++kk) {
+      const float2 h = hs[kb + kk];
+#pragma unroll
+      for (int s = 0; s < kFirS; ++s) cx_fma(acc[s], h, w[(s - kk) & (kFirS - 1)]);
+      // slide: x[n0 - k - 1] replaces the oldest window entry
+      const int k1 = kb + kk + 1;
+      float2 v = xs[fir_pad(base - k1)];
+      if (n0 - k1 < fstart) v = make_float2(0.0f, 0.0f);
+      w[(kFirS - 1 - kk) & (kFirS - 1)] = v;
+    }
+  }
+  if ((size_t)(n0 + kFirS) <= n && ((uintptr_t)(y + n0) % 16) == 0) {
+    float4* o = reinterpret_cast<float4*>(y + n0);
+#pragma unroll
+    for (int s = 0; s < kFirS; s += 2) st_stream(o + s / 2, make_float4(acc[s].x, acc[s].y, acc[s + 1].x, acc[s + 1].y));
+  } else {
+#pragma unroll
+    for (int s = 0; s < kFirS; ++s)
+      if ((size_t)(n0 + s) < n) y[n0 + s] = acc[s];
+  }
+}
+
+void launch_fir_direct(const float2* x, float2* y, size_t n, const float2* taps_padded, int tp, const float2* history,
+                       size_t frame_len, int, cudaStream_t st) {
+  if (n == 0) return;
+  const size_t n_in = (size_t)kFirTile + tp;
+  const size_t smem = ((size_t)tp + n_in + n_in / 8 + 2) * sizeof(float2);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(fir_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const unsigned grid = (unsigned)((n + kFirTile - 1) / kFirTile);
+  fir_direct_kernel<<<grid, kFirThreads, smem, st>>>(x, y, n, taps_padded, tp, history, frame_len);
+}
+
+// -------------------------------------------------------------------------------------------------
+// K4 overlap-save: one segment of NF inputs per frame slot -> FFT -> * H -> inverse FFT -> keep the
+// last L = NF - T + 1 outputs.  The forward transform's register layout (position t + m*T) is
+// exactly the inverse transform's input layout, so the spectrum never leaves registers.
+// H already carries the 1/NF of the round trip.  Flops/sample: (2*5*NF*log2 NF + 6*NF)/L.
+// -------------------------------------------------------------------------------------------------
+template <int NF>
+struct OsLaunch {
+  static constexpr int T = FftCfg<NF>::T;
+  static constexpr int F = T >= 256 ? 1 : (256 / T);
+  static constexpr int THREADS = F * T;
+  static constexpr size_t SMEM = (size_t)F * FftCfg<NF>::SMEM_ELEMS * sizeof(float2);
+};
+
+template <int NF>
+__global__ void __launch_bounds__(OsLaunch<NF>::THREADS)
+fir_os_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_t n, const float2* __restrict__ H,
+              const float2* __restrict__ tw, int ntaps, int hist_len, const float2* __restrict__ history, size_t frame_len,
+              size_t segs_per_frame, size_t n_segs) {
+  using C = FftCfg<NF>;
+  using LC = OsLaunch<NF>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* sm = reinterpret_cast<float2*>(smem_raw) + (threadIdx.x / C::T) * C::SMEM_ELEMS;
+  const int f = threadIdx.x / C::T;
+  const int t = threadIdx.x % C::T;
+  const size_t seg = (size_t)blockIdx.x * LC::F + f;
+  if (seg >= n_segs) return;
+  const long long L = NF - ntaps + 1;
+  long long out_start, frame_start, out_end;
+  if (frame_len) {
+    const size_t fi = seg / segs_per_frame, si = seg % segs_per_frame;
+    frame_start = (long long)(fi * frame_len);
+    out_start = frame_start + (long long)si * L;
+    long long fe = frame_start + (long long)frame_len;
+    if (fe > (long long)n) fe = (long long)n;
+    out_end = out_start + L < fe ? out_start + L : fe;
+  } else {
+    frame_start = 0;
+    out_start = (long long)seg * L;
+    out_end = out_start + L < (long long)n ? out_start + L : (long long)n;
+  }
+  const long long in_start = out_start - (ntaps - 1);
+  float2 v[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const long long g = in_start + t + m * C::T;
+    float2 s = make_float2(0.0f, 0.0f);
+    if (g >= frame_start) { if (g < out_end) s = ld_stream(x + g); }
+    else if (!frame_len && history && g >= -(long long)hist_len) s = __ldg(history + hist_len + g);
+    v[m] = s;
+  }
+  fft_frame<NF, false>(v, sm, tw, t, f);
+#pragma unroll
+  for (int m = 0; m < 16; ++m) v[m] = cx_mul(v[m], __ldg(H + t + m * C::T));
+  frame_sync<C::T>(f);  // every thread is past its last read of sm
+  fft_frame<NF, true>(v, sm, tw, t, f);
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const int i = t + m * C::T;
+    const long long g = out_start + i - (ntaps - 1);
+    if (i >= ntaps - 1 && g < out_end) st_stream(y + g, v[m]);
+  }
+}
+
+bool fir_os_supported(size_t nfft) { return nfft >= 256 && nfft <= 16384 && (nfft & (nfft - 1)) == 0; }
+
+template <int NF>
+static void launch_os_n(const float2* x, float2* y, size_t n, const float2* H, const float2* tw, size_t ntaps,
+                        const float2* history, int hist_len, size_t frame_len, cudaStream_t st) {
+  using LC = OsLaunch<NF>;
+  const size_t L = NF - ntaps + 1;
+  size_t segs_per_frame = 0, n_segs;
+  if (frame_len) {
+    segs_per_frame = (frame_len + L - 1) / L;
+    n_segs = ((n + frame_len - 1) / frame_len) * segs_per_frame;
+  } else {
+    n_segs = (n + L - 1) / L;
+  }
+  if (LC::SMEM > 48 * 1024) cudaFuncSetAttribute(fir_os_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
+  const unsigned grid = (unsigned)((n_segs + LC::F - 1) / LC::F);
+  fir_os_kernel<NF><<<grid, LC::THREADS, LC::SMEM, st>>>(x, y, n, H, tw, (int)ntaps, hist_len, history, frame_len, segs_per_frame, n_segs);
+}
+
+void launch_fir_overlap_save(const float2* x, float2* y, size_t n, const float2* H, const float2* tw, size_t nfft, size_t ntaps,
+                             const float2* history, size_t frame_len, cudaStream_t st) {
+  if (n == 0) return;
+  // history layout is shared with the direct kernel: (ntaps rounded up to 8) - 1 samples, newest last
+  const int hist_len = (int)(((ntaps + 7) / 8) * 8) - 1;
+  switch (nfft) {
+#define AE_CASE(NN) case NN: launch_os_n<NN>(x, y, n, H, tw, ntaps, history, hist_len, frame_len, st); break;
+    AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096) AE_CASE(8192) AE_CASE(16384)
+#undef AE_CASE
+    default: break;
+  }
+}
+
+}  // namespace ae

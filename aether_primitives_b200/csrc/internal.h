@@ -1,0 +1,83 @@
+// internal.h — launcher interface between the host API (api.cu) and the kernel TUs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "../../include/aether_b200.h"
+
+namespace ae {
+
+// ---- K1 fused VecOps tape -------------------------------------------------------------------
+enum TapeOpcode : int { OP_SCALE = 0, OP_MUL, OP_DIV, OP_ADD, OP_SUB, OP_CONJ, OP_MIRROR, OP_CLONE, OP_ZERO };
+constexpr int kMaxTape = 16;
+struct TapeEntry {
+  const float2* operand;  // other[] for MUL/DIV/ADD/SUB/CLONE
+  float s;                // SCALE factor
+  int op;
+};
+struct TapeParams {
+  TapeEntry e[kMaxTape];
+  int n_ops;
+  int load_self;  // 0 when a ZERO/CLONE precedes every use of the old contents
+};
+void launch_vecops(float2* v, size_t n, const TapeParams& p, bool has_mirror, int sm_count, cudaStream_t st);
+
+// ---- K5/K6 sampling --------------------------------------------------------------------------
+void launch_downsample_cf32(const float2* src, float2* dst, size_t n_dst, size_t dec, cudaStream_t st);
+void launch_downsample_u8(const uint8_t* src, uint8_t* dst, size_t n_dst, size_t dec, cudaStream_t st);
+void launch_interpolate(const float2* src, size_t n_src, float2* dst, size_t n_between, int compat, cudaStream_t st);
+
+// ---- K7/K8 modulation ------------------------------------------------------------------------
+struct ModTable { float2 t[4]; int len; };
+void launch_modulate(const ModTable& tab, const uint8_t* bits, size_t nbits, float2* out, size_t n_out,
+                     int* errflag, cudaStream_t st);
+void launch_demod(const ModTable& tab, const float2* sym, size_t n, uint8_t* bits, int compat, cudaStream_t st);
+
+// ---- K9/K10 noise ----------------------------------------------------------------------------
+void launch_awgn_fill(float2* dst, size_t n, float scale, uint64_t seed, uint64_t stream, uint64_t offset, cudaStream_t st);
+void launch_awgn_apply(float2* sig, size_t n, float scale, int twice, uint64_t seed, uint64_t stream, uint64_t offset,
+                       cudaStream_t st);
+void launch_modem_fused(const ModTable& tab, const uint8_t* bits_in, size_t nbits, uint8_t* bits_out, float scale,
+                        int twice, uint64_t seed, uint64_t stream, uint64_t offset, int compat, ae_stats* stats,
+                        int* errflag, int sm_count, cudaStream_t st);
+
+// ---- K11 sequence ----------------------------------------------------------------------------
+void launch_expand(uint64_t seed, size_t len, uint8_t* out, cudaStream_t st);
+// state = first `deg` bits of the recurrence window (bit i = x[base+i]); poly_low = coefficients of
+// x^0..x^(deg-1) of the characteristic polynomial; writes out[0..len) = x[base + 0 ...]
+void launch_mseq(uint64_t state, uint64_t poly_low, int deg, size_t len, uint8_t* out, cudaStream_t st);
+
+// ---- K13 statistics --------------------------------------------------------------------------
+void launch_bit_errors(const uint8_t* a, const uint8_t* b, size_t n, ae_stats* stats, int sm_count, cudaStream_t st);
+void launch_evm_acc(const float2* act, const float2* ref, size_t n, ae_stats* stats, int sm_count, cudaStream_t st);
+
+// ---- K2 FFT ----------------------------------------------------------------------------------
+// power-of-two register/shared-memory kernel, 16 <= n <= 16384.  tw[k] = exp(-2 pi i k/n).
+bool fft_pow2_supported(size_t n);
+void launch_fft_pow2(const float2* in, float2* out, size_t n, size_t frames, const float2* tw, bool inverse,
+                     bool do_scale, float scale, cudaStream_t st);
+// any length: one global-memory Stockham pass per prime-power factor; needs 2 scratch buffers
+void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n, size_t frames, const float2* tw,
+                        const uint32_t* radices, int n_radices, bool inverse, bool do_scale, float scale,
+                        cudaStream_t st);
+int fft_launches_pow2();
+// ---- K3/K4 FIR -------------------------------------------------------------------------------
+void launch_fir_direct(const float2* x, float2* y, size_t n, const float2* taps_padded, int ntaps_padded,
+                       const float2* history /*ntaps_padded-1 samples or null*/, size_t frame_len, int sm_count,
+                       cudaStream_t st);
+bool fir_os_supported(size_t nfft);
+// H = FFT_nfft(taps)/nfft (exp(-) convention); L = nfft - ntaps + 1 outputs per segment
+void launch_fir_overlap_save(const float2* x, float2* y, size_t n, const float2* H, const float2* tw, size_t nfft,
+                             size_t ntaps, const float2* history, size_t frame_len, cudaStream_t st);
+// ---- K14 / K12 chains ------------------------------------------------------------------------
+bool chain_fused_supported(size_t nfft, size_t ntaps);
+// window[n] = s * sum_k h[k] exp(-sgn 2 pi i nk/N); taps in device memory
+void launch_chain_fused(const float2* x, uint8_t* bits, size_t nfft, size_t frames, const float2* window,
+                        const float2* taps, size_t ntaps, const float2* tw, bool inverse, float scale, int compat,
+                        cudaStream_t st);
+bool ofdm_supported(size_t nfft);
+void launch_ofdm_chain(size_t nfft, size_t frames, uint64_t first_frame, float noise_scale, int twice, uint64_t seed,
+                       const float2* tw, int compat, uint8_t* tx_bits, uint8_t* rx_bits, ae_stats* stats,
+                       cudaStream_t st);
+
+}  // namespace ae

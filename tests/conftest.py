@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def ora():
+    from tests import oracle
+
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def ae():
+    """The CUDA package, initialised on device 0.  Only -m gpu tests may request this."""
+    import aether_primitives_b200 as pkg
+
+    pkg.init(0)
+    return pkg
