@@ -18,7 +18,7 @@ from .vecops import DeviceBits, DeviceVec
 
 def modem_fused(m: Modulation, awgn: Awgn, bits_in: DeviceBits, bits_out: DeviceBits, stats: DeviceStats | None = None,
                 compat: int = _lib.COMPAT_REFERENCE) -> None:
-    call("ae_modem_fused", m._h, awgn._h, bits_in._h, bits_out._h, stats._h if stats else None, compat)
+    call("ae_modem_fused", m._h, awgn._h, bits_in._h, bits_out._h, stats._h if stats is not None else None, compat)
 
 
 class FftFirDemod:
@@ -35,7 +35,7 @@ class FftFirDemod:
         call("ae_chain_exec", self._h, input._h, bits_out._h)
 
     def run_unfused(self, input: DeviceVec, bits_out: DeviceBits, symbols_out: DeviceVec | None = None) -> None:
-        call("ae_chain_exec_unfused", self._h, input._h, bits_out._h, symbols_out._h if symbols_out else None)
+        call("ae_chain_exec_unfused", self._h, input._h, bits_out._h, symbols_out._h if symbols_out is not None else None)
 
     def run_host(self, host_in_ptr: int, n_samples: int, host_bits_ptr: int) -> None:
         """HOST buffers (ideally pinned): chunked H2D -> kernel -> D2H pipeline inside the call."""
@@ -54,4 +54,4 @@ def ofdm_chain(fft_len: int, frames: int, first_frame_id: int, noise_power: floa
                stats: DeviceStats | None, tx_bits: DeviceBits | None = None, rx_bits: DeviceBits | None = None,
                compat: int = _lib.COMPAT_REFERENCE) -> None:
     call("ae_ofdm_chain", fft_len, frames, C.c_uint64(first_frame_id), C.c_float(noise_power), C.c_uint64(noise_seed), compat,
-         tx_bits._h if tx_bits else None, rx_bits._h if rx_bits else None, stats._h if stats else None)
+         tx_bits._h if tx_bits is not None else None, rx_bits._h if rx_bits is not None else None, stats._h if stats is not None else None)

@@ -32,12 +32,13 @@ chain_fused_kernel(const float2* __restrict__ x, uint8_t* __restrict__ bits, siz
   using C = FftCfg<N>;
   using LC = ChainLaunch<N>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [taps: ntaps][per frame: fft buffer SMEM_ELEMS | tail: ntaps]
+  // layout: [taps: ntaps][per frame: fft buffer A | fft buffer B | tail: ntaps]
   float2* hs = reinterpret_cast<float2*>(smem_raw);
   const int f = threadIdx.x / C::T;
   const int t = threadIdx.x % C::T;
-  float2* sm = hs + ntaps + (size_t)f * (C::SMEM_ELEMS + ntaps);
-  float2* tail = sm + C::SMEM_ELEMS;  // tail[i] = scale * A[N - (ntaps-1) + i]
+  float2* smA = hs + ntaps + (size_t)f * (2 * C::SMEM_ELEMS + ntaps);
+  float2* smB = smA + C::SMEM_ELEMS;
+  float2* tail = smB + C::SMEM_ELEMS;  // tail[i] = scale * A[N - (ntaps-1) + i]
   for (int i = threadIdx.x; i < ntaps; i += LC::THREADS) hs[i] = __ldg(taps + i);
   __syncthreads();
   const size_t frame = (size_t)blockIdx.x * LC::F + f;
@@ -45,29 +46,30 @@ chain_fused_kernel(const float2* __restrict__ x, uint8_t* __restrict__ bits, siz
   const float2* src = x + frame * N;
   const int tm1 = ntaps - 1;
 
-  float2 a[16], b[16];
+  // ab[0] = x (-> A = DFT(x)), ab[1] = x .* w (-> B = circular convolution of scale*X with h);
+  // both transforms advance pass by pass together: twiddles loaded once, barriers shared
+  float2 ab[2][16];
 #pragma unroll
-  for (int m = 0; m < 16; ++m) a[m] = ld_stream(src + t + m * C::T);
+  for (int m = 0; m < 16; ++m) ab[0][m] = ld_stream(src + t + m * C::T);
 #pragma unroll
-  for (int m = 0; m < 16; ++m) b[m] = cx_mul(a[m], __ldg(window + t + m * C::T));
+  for (int m = 0; m < 16; ++m) ab[1][m] = cx_mul(ab[0][m], __ldg(window + t + m * C::T));
+  float2* const sm2[2] = {smA, smB};
+  fft_frames<N, INV, 2>(ab, sm2, tw, t, f);
 
-  // A = DFT(x): only its last T-1 bins are kept (scaled like Cfft::fwd's output)
-  fft_frame<N, INV>(a, sm, tw, t, f);
+  // only the last T-1 bins of A are needed (scaled like Cfft::fwd's output)
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
     const int pos = t + m * C::T;
-    if (pos >= N - tm1) tail[pos - (N - tm1)] = cx_scale_exact(a[m], scale);
+    if (pos >= N - tm1) tail[pos - (N - tm1)] = cx_scale_exact(ab[0][m], scale);
   }
-  frame_sync<C::T>(f);  // tail visible; everyone is past the last read of sm
-  // B = DFT(x .* w) = circular convolution of scale*X with h
-  fft_frame<N, INV>(b, sm, tw, t, f);
+  frame_sync<C::T>(f);
 
-  float2 tab[4] = {make_float2(1.0f, 1.0f), make_float2(-1.0f, 1.0f), make_float2(1.0f, -1.0f), make_float2(-1.0f, -1.0f)};
+  const float2 tab[4] = {make_float2(1.0f, 1.0f), make_float2(-1.0f, 1.0f), make_float2(1.0f, -1.0f), make_float2(-1.0f, -1.0f)};
   uint8_t* out = bits + 2 * frame * (size_t)N;
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
     const int n = t + m * C::T;
-    float2 yv = b[m];
+    float2 yv = ab[1][m];
     if (n < tm1) {  // wrap-around terms of the circular convolution
       float2 acc = make_float2(0.0f, 0.0f);
       for (int k = n + 1; k <= tm1; ++k) cx_fma(acc, hs[k], tail[n - k + tm1]);
@@ -88,7 +90,7 @@ template <int N>
 static void launch_chain_n(const float2* x, uint8_t* bits, size_t frames, const float2* window, const float2* taps,
                            size_t ntaps, const float2* tw, bool inverse, float scale, int compat, cudaStream_t st) {
   using LC = ChainLaunch<N>;
-  const size_t smem = (ntaps + (size_t)LC::F * (FftCfg<N>::SMEM_ELEMS + ntaps)) * sizeof(float2);
+  const size_t smem = (ntaps + (size_t)LC::F * (2 * FftCfg<N>::SMEM_ELEMS + ntaps)) * sizeof(float2);
   const unsigned grid = (unsigned)((frames + LC::F - 1) / LC::F);
   if (inverse) {
     cudaFuncSetAttribute(chain_fused_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,4 +1,4 @@
-// fft_device.cuh — in-register / shared-memory Stockham FFT for one power-of-two frame.
+// fft_device.cuh — in-register / shared-memory Stockham FFT for power-of-two frames.
 //
 // Replaces the rustfft call under Cfft::{fwd,bwd,ifwd,ibwd,tfwd,tbwd} (src/fft.rs:162-230).
 //
@@ -16,9 +16,18 @@
 //     out position = (j - k)*R + k + r*NS                     (Stockham autosort)
 // Between passes the 16 values go through shared memory (one cf32 of padding per 16 so the
 // stride-16 stores of the first pass are bank-conflict free); the last pass leaves them in
-// registers.  Twiddles come from a table tw[k] = exp(-2 pi i k/N) computed in f64 on the host
-// and rounded to f32 (same accuracy class as rustfft), read through the read-only path.
+// registers.
+//
+// Twiddles come from a table tw[k] = exp(-2 pi i k/N) computed in f64 on the host and rounded to
+// f32 (rustfft's accuracy class).  Table reads are scattered 8-byte loads that cost L1 wavefronts,
+// and the first profile of the fused chain showed the LSU data pipe at 81 % because of them, so
+//   * a radix-16 pass loads only W^1,W^2,W^3 and W^4,W^8,W^12 and forms W^(4a+b) = W^(4a) W^b;
+//   * the last (radix-2^REM) pass has k = t + q*T, so W^(r k) = W^(r t) * W16^(r q): R-1 loads,
+//     the rest are compile-time constants;
+//   * NB frames that share the thread mapping (the two transforms of the fused chain) are run
+//     pass by pass TOGETHER so every twiddle is loaded once and every barrier is shared.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace ae {
@@ -57,6 +66,28 @@ __device__ __forceinline__ float2 mul_tw(float2 a, float2 w) {
   return INV ? cx_mul_conj(a, w) : cx_mul(a, w);
 }
 
+constexpr float kC8 = 0.70710678118654752440f;   // cos(pi/4)
+constexpr float kC16 = 0.92387953251128675613f;  // cos(pi/8)
+constexpr float kS16 = 0.38268343236508977173f;  // sin(pi/8)
+
+// a * W16^E (forward) or its conjugate (inverse), E known at compile time
+template <int E, bool INV>
+__device__ __forceinline__ float2 mul_w16(float2 a) {
+  constexpr int e = ((E % 16) + 16) % 16;
+  if constexpr (e == 0) return a;
+  else if constexpr (e == 4) return mul_mi<INV>(a);
+  else if constexpr (e == 8) return make_float2(-a.x, -a.y);
+  else if constexpr (e == 12) return mul_mi<!INV>(a);
+  else {
+    // cos / sin of 2 pi e / 16
+    constexpr float c = (e == 1 || e == 15) ? kC16 : (e == 2 || e == 14) ? kC8 : (e == 3 || e == 13) ? kS16
+                        : (e == 5 || e == 11) ? -kS16 : (e == 6 || e == 10) ? -kC8 : -kC16;  // e == 7 || e == 9
+    constexpr float s = (e == 1 || e == 7) ? kS16 : (e == 2 || e == 6) ? kC8 : (e == 3 || e == 5) ? kC16
+                        : (e == 9 || e == 15) ? -kS16 : (e == 10 || e == 14) ? -kC8 : -kC16;  // e == 11 || e == 13
+    return mul_w<INV>(a, c, s);
+  }
+}
+
 template <bool INV>
 __device__ __forceinline__ void dft2(float2& a, float2& b) {
   const float2 s = cx_add(a, b), d = cx_sub(a, b);
@@ -68,10 +99,6 @@ __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2&
   const float2 s2 = cx_add(a1, a3), s3 = mul_mi<INV>(cx_sub(a1, a3));
   a0 = cx_add(s0, s2); a1 = cx_add(s1, s3); a2 = cx_sub(s0, s2); a3 = cx_sub(s1, s3);
 }
-
-constexpr float kC8 = 0.70710678118654752440f;   // cos(pi/4)
-constexpr float kC16 = 0.92387953251128675613f;  // cos(pi/8)
-constexpr float kS16 = 0.38268343236508977173f;  // sin(pi/8)
 
 // natural-order in, natural-order out DFTs on register arrays
 template <int R, bool INV> struct Dft;
@@ -89,9 +116,9 @@ template <bool INV> struct Dft<8, INV> {
   static __device__ __forceinline__ void run(float2 (&v)[8]) {
     dft4<INV>(v[0], v[2], v[4], v[6]);  // b = 0 -> Y0[c] in v[2c]
     dft4<INV>(v[1], v[3], v[5], v[7]);  // b = 1 -> Y1[c] in v[2c+1]
-    v[3] = mul_w<INV>(v[3], kC8, kC8);                 // W8^1
-    v[5] = mul_mi<INV>(v[5]);                          // W8^2 = -i
-    v[7] = mul_w<INV>(v[7], -kC8, kC8);                // W8^3
+    v[3] = mul_w16<2, INV>(v[3]);       // W8^1
+    v[5] = mul_w16<4, INV>(v[5]);       // W8^2 = -i
+    v[7] = mul_w16<6, INV>(v[7]);       // W8^3
     float2 o[8];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -107,16 +134,15 @@ template <bool INV> struct Dft<16, INV> {
   static __device__ __forceinline__ void run(float2 (&v)[16]) {
 #pragma unroll
     for (int b = 0; b < 4; ++b) dft4<INV>(v[b], v[4 + b], v[8 + b], v[12 + b]);  // Y_b[c] in v[4c+b]
-    // W16^(b*c), b,c in 1..3
-    v[5] = mul_w<INV>(v[5], kC16, kS16);     // e=1
-    v[6] = mul_w<INV>(v[6], kC8, kC8);       // e=2
-    v[7] = mul_w<INV>(v[7], kS16, kC16);     // e=3
-    v[9] = mul_w<INV>(v[9], kC8, kC8);       // e=2
-    v[10] = mul_mi<INV>(v[10]);              // e=4
-    v[11] = mul_w<INV>(v[11], -kC8, kC8);    // e=6
-    v[13] = mul_w<INV>(v[13], kS16, kC16);   // e=3
-    v[14] = mul_w<INV>(v[14], -kC8, kC8);    // e=6
-    v[15] = mul_w<INV>(v[15], -kC16, -kS16); // e=9: cos=-c16, sin(2pi*9/16) = -s16
+    v[5] = mul_w16<1, INV>(v[5]);
+    v[6] = mul_w16<2, INV>(v[6]);
+    v[7] = mul_w16<3, INV>(v[7]);
+    v[9] = mul_w16<2, INV>(v[9]);
+    v[10] = mul_w16<4, INV>(v[10]);
+    v[11] = mul_w16<6, INV>(v[11]);
+    v[13] = mul_w16<3, INV>(v[13]);
+    v[14] = mul_w16<6, INV>(v[14]);
+    v[15] = mul_w16<9, INV>(v[15]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) dft4<INV>(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);  // X[c+4d] in v[4c+d]
     float2 o[16];
@@ -129,10 +155,19 @@ template <bool INV> struct Dft<16, INV> {
   }
 };
 
-// one pass; LAST leaves the result in x (register m <-> position t + m*T), otherwise it is
-// written to the padded shared-memory frame `sm`
-template <int N, int P, bool INV>
-__device__ __forceinline__ void fft_pass(float2 (&x)[16], float2* __restrict__ sm, const float2* __restrict__ tw, int t) {
+// compile-time loop helper: f(integral_constant<int, I>) for I in [0, N)
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// one pass over NB frames that share thread mapping and twiddles.  LAST leaves the result in x
+// (register m <-> position t + m*T), otherwise it is written to the padded shared frames sm[b].
+template <int N, int P, bool INV, int NB>
+__device__ __forceinline__ void fft_pass(float2 (&x)[NB][16], float2* const (&sm)[NB], const float2* __restrict__ tw, int t) {
   using C = FftCfg<N>;
   constexpr int R = C::radix(P);
   constexpr int NS = C::ns(P);
@@ -140,34 +175,88 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[16], float2* __restrict__ s
   constexpr int T = C::T;
   constexpr bool LAST = (P == C::NP - 1);
   constexpr int TWS = N / (NS * R);
+  if constexpr (R == 16) {
+    const int k = t & (NS - 1);
+    float2 v[NB][16];
 #pragma unroll
-  for (int q = 0; q < B; ++q) {
-    float2 v[R];
+    for (int b = 0; b < NB; ++b)
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = x[q + B * r];
-    const int j = t + q * T;
-    const int k = j & (NS - 1);
-    if (NS > 1) {
+      for (int r = 0; r < 16; ++r) v[b][r] = x[b][r];
+    if constexpr (NS > 1) {
+      const int u = k * TWS;
+      float2 wl[4], wh[4];  // W^b (b = 1..3) and W^(4a) (a = 1..3)
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[r] = mul_tw<INV>(v[r], __ldg(tw + r * k * TWS));
+      for (int i = 1; i < 4; ++i) { wl[i] = __ldg(tw + i * u); wh[i] = __ldg(tw + 4 * i * u); }
+#pragma unroll
+      for (int r = 1; r < 16; ++r) {
+        const int a = r >> 2, bb = r & 3;
+        float2 w;
+        if (a == 0) w = wl[bb];
+        else if (bb == 0) w = wh[a];
+        else w = cx_mul(wh[a], wl[bb]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) v[b][r] = mul_tw<INV>(v[b][r], w);
+      }
     }
-    Dft<R, INV>::run(v);
-    if (LAST) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) x[q + B * r] = v[r];
+    for (int b = 0; b < NB; ++b) Dft<16, INV>::run(v[b]);
+    if constexpr (LAST) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[b][r] = v[b][r];
     } else {
-      const int base = (j - k) * R + k;
+      // padded address of position (t-k)*16 + k + r*NS is linear in r
+      int a0;
+      constexpr int STEP = (NS == 1) ? 1 : (NS + NS / 16);
+      if constexpr (NS == 1) a0 = 17 * t;
+      else a0 = fft_pad((t - k) * 16 + k);
 #pragma unroll
-      for (int r = 0; r < R; ++r) sm[fft_pad(base + r * NS)] = v[r];
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sm[b][a0 + r * STEP] = v[b][r];
     }
+  } else {
+    // last pass, radix R < 16, B = 16/R butterflies per thread; k = j = t + q*T, TWS == 1
+    static_assert(LAST && TWS == 1, "sub-radix pass must be the last one");
+    float2 wt[R];  // W^(r t)
+#pragma unroll
+    for (int r = 1; r < R; ++r) wt[r] = __ldg(tw + r * t);
+    static_for<0, B>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        float2 v[R];
+        v[0] = x[b][q];
+        static_for<1, R>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          // W^(r (t + q T)) = W^(r t) * W16^(r q)   (T = N/16)
+          v[r] = mul_w16<r * q, INV>(mul_tw<INV>(x[b][q + B * r], wt[r]));
+        });
+        Dft<R, INV>::run(v);
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[b][q + B * r] = v[r];
+      }
+    });
   }
 }
 
-template <int N>
-__device__ __forceinline__ void fft_load_smem(float2 (&x)[16], const float2* __restrict__ sm, int t) {
+template <int N, int NB>
+__device__ __forceinline__ void fft_load_smem(float2 (&x)[NB][16], float2* const (&sm)[NB], int t) {
   constexpr int T = FftCfg<N>::T;
+  if constexpr (T % 16 == 0) {
+    const int a0 = fft_pad(t);
+    constexpr int STEP = T + T / 16;
 #pragma unroll
-  for (int m = 0; m < 16; ++m) x[m] = sm[fft_pad(t + m * T)];
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int m = 0; m < 16; ++m) x[b][m] = sm[b][a0 + m * STEP];
+  } else {
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int m = 0; m < 16; ++m) x[b][m] = sm[b][fft_pad(t + m * T)];
+  }
 }
 
 // barrier among the T threads that own one frame (frame slot f of the CTA)
@@ -178,24 +267,36 @@ __device__ __forceinline__ void frame_sync(int f) {
   else asm volatile("bar.sync %0, %1;" ::"r"(f + 1), "r"(T) : "memory");
 }
 
-template <int N, int P, bool INV>
-__device__ __forceinline__ void fft_passes_from(float2 (&x)[16], float2* __restrict__ sm, const float2* __restrict__ tw, int t, int f) {
+template <int N, int P, bool INV, int NB>
+__device__ __forceinline__ void fft_passes_from(float2 (&x)[NB][16], float2* const (&sm)[NB], const float2* __restrict__ tw, int t, int f) {
   using C = FftCfg<N>;
-  fft_pass<N, P, INV>(x, sm, tw, t);
+  fft_pass<N, P, INV, NB>(x, sm, tw, t);
   if constexpr (P + 1 < C::NP) {
     frame_sync<C::T>(f);
-    fft_load_smem<N>(x, sm, t);
+    fft_load_smem<N, NB>(x, sm, t);
     if constexpr (P + 2 < C::NP) frame_sync<C::T>(f);  // WAR: the next pass stores into sm again
-    fft_passes_from<N, P + 1, INV>(x, sm, tw, t, f);
+    fft_passes_from<N, P + 1, INV, NB>(x, sm, tw, t, f);
   }
 }
 
-// Full transform of one frame.  x: register m <-> position t + m*T (in and out).
+// Full transform of NB frames at once.  x[b]: register m <-> position t + m*T (in and out).
 // The caller must make sure every thread of the frame is past its last shared-memory READ of a
-// previous use of `sm` (frame_sync) before calling this again with the same buffer.
+// previous use of the buffers (frame_sync) before calling this again with the same buffers.
+template <int N, bool INV, int NB>
+__device__ __forceinline__ void fft_frames(float2 (&x)[NB][16], float2* const (&sm)[NB], const float2* __restrict__ tw, int t, int f) {
+  fft_passes_from<N, 0, INV, NB>(x, sm, tw, t, f);
+}
+
+// single-frame convenience wrapper
 template <int N, bool INV>
-__device__ __forceinline__ void fft_frame(float2 (&x)[16], float2* __restrict__ sm, const float2* __restrict__ tw, int t, int f) {
-  fft_passes_from<N, 0, INV>(x, sm, tw, t, f);
+__device__ __forceinline__ void fft_frame(float2 (&x)[16], float2* __restrict__ smem, const float2* __restrict__ tw, int t, int f) {
+  float2* const sm[1] = {smem};
+  float2 y[1][16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) y[0][m] = x[m];
+  fft_frames<N, INV, 1>(y, sm, tw, t, f);
+#pragma unroll
+  for (int m = 0; m < 16; ++m) x[m] = y[0][m];
 }
 
 }  // namespace ae

@@ -3,7 +3,7 @@
 // The reference's src/fir.rs:1-22 is a constructor-only stub; the filter is the
 // textbook definition  y[n] = sum_{k<T} h[k] x[n-k],  output length = input length, with either
 // a carried history of T-1 samples (streaming) or zero state at the start of every frame.
-// Parity tier T1: EVM against the f64 direct form (oracle/aether_oracle.cpp ora_fir_f64).
+// Parity tier T1: EVM against the f64 direct form (tests/test_gpu_fir.py).
 #include "fft_device.cuh"
 #include "internal.h"
 

@@ -27,7 +27,10 @@ def use_torch_stream() -> None:
     """Issue all library work on torch's current CUDA stream (so torch.cuda.Event times it)."""
     import torch
 
-    set_stream(torch.cuda.current_stream().cuda_stream)
+    ptr = torch.cuda.current_stream().cuda_stream
+    # torch's default stream is the legacy NULL stream: name it explicitly (cudaStreamLegacy = 0x1),
+    # because ae_set_stream(NULL) means "the library's own stream"
+    set_stream(ptr if ptr else 0x1)
 
 
 def sync() -> None:

@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 cf32 path.
+
+Workload (BASELINE.json metric): batched 1024-point cf32 Cfft::fwd(Scale::SN) -> 64-tap complex
+FIR (zero state per frame) -> QPSK hard demod, 2^20 frames per GPU, synthetic N(0,1) input.
+One "step" = one pass of the fused chain kernel over the whole batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F] [--no-extras]
+
+For N > 1 launch with torchrun (one rank per GPU); frames are sharded, no data-path collective
+(weak scaling: every rank owns 2^20 frames).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FFT_LEN = 1024
+NTAPS = 64
+ALG_BYTES_PER_SAMPLE = 10.0   # 8 B cf32 in + 2 B bits out (SURVEY §8d headline row)
+FLOP_PER_SAMPLE = 2 * 50 + 6 + 16  # two 1024-pt FFTs + window multiply + triangular fix-up
+METRIC = "cf32 Gsamples/s, FFT->FIR->QPSK-demod chain (1024-pt fwd FFT, 64-tap FIR, hard demod)"
+
+
+def make_taps(t: int = NTAPS) -> np.ndarray:
+    """windowed-sinc * exp(j phi), unit DC gain, seed 3"""
+    rng = np.random.default_rng(3)
+    k = np.arange(t) - (t - 1) / 2
+    h = np.sinc(k / 4.0) * np.hamming(t) * np.exp(1j * rng.uniform(0, 2 * np.pi))
+    return (h / np.abs(h.sum())).astype(np.complex64)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.25] or [l for (_, l) in self.lines]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+                for name, val in zip(names, f[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's algorithm, all host threads, bounded sample
+# ---------------------------------------------------------------------------------------------------
+def cpu_chain_rate(target_seconds: float, threads: int, steps: int = 1, warmup: int = 0):
+    """Times tests.oracle.chain_fft_fir_demod (C++ restatement of the reference, frame-parallel
+    std::thread) on a sample sized for ~target_seconds per step.  Returns (Gsamples/s, ms/step, frames)."""
+    from tests import oracle as o
+
+    taps = make_taps()
+    rng = np.random.default_rng(1)
+    cal = 64 * threads
+    x = (rng.standard_normal(cal * FFT_LEN) + 1j * rng.standard_normal(cal * FFT_LEN)).astype(np.complex64)
+    o.chain_fft_fir_demod(x, FFT_LEN, taps, nthreads=threads, want_symbols=False)
+    t0 = time.perf_counter()
+    o.chain_fft_fir_demod(x, FFT_LEN, taps, nthreads=threads, want_symbols=False)
+    dt = time.perf_counter() - t0
+    frames = int(max(cal, min(1 << 20, cal * target_seconds / max(dt, 1e-6))))
+    frames = (frames // threads) * threads
+    x = (rng.standard_normal(frames * FFT_LEN) + 1j * rng.standard_normal(frames * FFT_LEN)).astype(np.complex64)
+    for _ in range(warmup):
+        o.chain_fft_fir_demod(x, FFT_LEN, taps, nthreads=threads, want_symbols=False)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.chain_fft_fir_demod(x, FFT_LEN, taps, nthreads=threads, want_symbols=False)
+    dt = (time.perf_counter() - t0) / steps
+    return frames * FFT_LEN / dt / 1e9, dt * 1e3, frames
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # bounded sample: ~2 s of CPU work per step so that steps+warmup finish within minutes
+    per_step = max(0.5, min(3.0, 120.0 / max(1, args.steps + args.warmup)))
+    gs, ms, frames = cpu_chain_rate(per_step, threads, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gs, "unit": "Gsamples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "fft1024_fwd_SN -> fir64 -> qpsk_demod", "fft_len": FFT_LEN, "ntaps": NTAPS,
+                   "frames_per_step": frames, "note": "reference crate is Rust and cannot be built here; this is the C++ restatement (oracle port), not rustfft"},
+        "cpu_baseline": {"value": gs, "unit": "Gsamples/s", "cores": threads, "kind": "port",
+                         "sample": "%d frames x %d samples per step, %d host threads" % (frames, FFT_LEN, threads)},
+        "e2e": {"value": gs, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def timed(torch, fn, steps: int, warmup: int, barrier=None):
+    """W warm-ups, then exactly `steps` calls bracketed by barrier + synchronize; CUDA events on the
+    launching stream.  Returns seconds for all steps."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return e0.elapsed_time(e1) / 1e3
+
+
+def extras(torch, ae, d_in, frames, hbm_peak, steps=5, warmup=3):
+    """Stand-alone kernels of the other BASELINE configs, device-timed, each with its algorithmic
+    bytes and fraction of the measured HBM peak.  Reported for information under "extra"."""
+    from aether_primitives_b200 import fir as F
+    from aether_primitives_b200.stats import DeviceStats
+
+    out = {}
+    n = frames * FFT_LEN
+
+    def rec(name, alg_bytes, secs, units, unit_name):
+        gbs = alg_bytes / secs / 1e9
+        out[name] = {"ms": secs * 1e3, "G%s/s" % unit_name: units / secs / 1e9, "alg_GB/s": gbs, "frac_hbm": gbs / hbm_peak}
+
+    fft = ae.Cfft.with_len(FFT_LEN)
+    # config 2: forward + backward 1024-pt FFT with scaling, in place
+    t = timed(torch, lambda: (fft.ifwd(d_in, ae.Scale.SN, howmany=frames), fft.ibwd(d_in, ae.Scale.SN, howmany=frames)), steps, warmup) / steps
+    rec("fft1024_fwd+bwd_SN", 32.0 * n, t, n, "samples")
+    out["fft1024_fwd+bwd_SN"]["fft_TFLOP/s"] = 2 * 5 * FFT_LEN * 10 * frames / t / 1e12
+    t = timed(torch, lambda: fft.ifwd(d_in, ae.Scale.SN, howmany=frames), steps, warmup) / steps
+    rec("fft1024_fwd_SN", 16.0 * n, t, n, "samples")
+    # config 4: fused mul.conj.mirror, downsample/4, interpolate x4 on 2^28 samples
+    m = min(n, 1 << 28)
+    a = d_in.view(0, m)
+    b = ae.DeviceVec.zeros(m)
+    t = timed(torch, lambda: a.vec_mul(b).vec_conj().vec_mirror().flush(), steps, warmup) / steps
+    rec("vecops_mul_conj_mirror_fused", 24.0 * m, t, m, "samples")
+    ds = ae.DeviceVec.zeros(m // 4)
+    t = timed(torch, lambda: ae.sampling.downsample(a, ds), steps, warmup) / steps
+    rec("downsample_by4", 16.0 * (m // 4), t, m // 4, "outputs")
+    src = d_in.view(0, m // 4)
+    dst = ae.DeviceVec.with_capacity(m)
+
+    def interp():
+        dst.clear()
+        ae.sampling.interpolate(src, dst, 3)
+    t = timed(torch, interp, steps, warmup) / steps
+    rec("interpolate_x4", 40.0 * (m // 4), t, m // 4, "inputs")
+    del dst, ds
+    # config 3: 64-tap FIR direct and overlap-save, 1024-tap overlap-save, 2^28 samples (b is the output)
+    taps64 = make_taps(64)
+    for name, filt in (("fir64_direct", F.Fir(taps64, F.DIRECT)), ("fir64_overlap_save", F.Fir(taps64, F.OVERLAP_SAVE)),
+                       ("fir1024_overlap_save", F.Fir(make_taps(1024), F.OVERLAP_SAVE))):
+        t = timed(torch, lambda: filt.filter(a, b), steps, warmup) / steps
+        rec(name, 16.0 * m, t, m, "samples")
+    # config 1: modem loop-back at 1M symbols (launch-bound) and 2^28 symbols
+    qpsk = ae.modulation.qpsk()
+    g = ae.noise.new(0.01, 815)
+    st = DeviceStats()
+    for nsym in (1_000_000, 1 << 28):
+        bits_in = ae.DeviceBits.zeros(2 * nsym)
+        bits_out = ae.DeviceBits.zeros(2 * nsym)
+        t = timed(torch, lambda: ae.chain.modem_fused(qpsk, g, bits_in, bits_out, st, ae.COMPAT_REFERENCE), steps, warmup) / steps
+        rec("modem_fused_%dsym" % nsym, 4.0 * nsym, t, nsym, "symbols")
+        del bits_in, bits_out
+    # config 5: OFDM-like chain, 2048-pt, 2^16 frames, counters only
+    fr = 1 << 16
+    t = timed(torch, lambda: ae.chain.ofdm_chain(2048, fr, 0, 0.05, 5, st), steps, warmup) / steps
+    out["ofdm2048_chain"] = {"ms": t * 1e3, "Gsymbols/s": fr * 2048 / t / 1e9, "bytes_note": "counters only; compute-bound by construction"}
+    return out
+
+
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+
+    import aether_primitives_b200 as ae
+    from aether_primitives_b200.chain import FftFirDemod
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ae.init(local_rank)
+    ae.use_torch_stream()
+    hbm_peak, peak_src = measured_peaks()
+
+    frames = args.frames
+    n = frames * FFT_LEN
+    taps = make_taps()
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1 + rank)
+    x = torch.view_as_complex(torch.randn(n, 2, device="cuda", dtype=torch.float32, generator=gen))
+    bits = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    d_in = ae.DeviceVec.from_torch(x)
+    d_bits = ae.DeviceBits.wrap(bits.data_ptr(), bits.numel(), owner=bits)
+    chain = FftFirDemod(FFT_LEN, taps, ae.Scale.SN, ae.COMPAT_REFERENCE)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+
+    def step():
+        chain.run(d_in, d_bits)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = ae.launch_count()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    l_warm = ae.launch_count() - l0
+    t_mark0 = sampler.mark()
+    l1 = ae.launch_count()
+    secs = timed(torch, step, args.steps, 0, barrier)
+    launches = ae.launch_count() - l1
+    t_mark1 = sampler.mark()
+    tt = torch.tensor([secs], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    secs_max = float(tt.item())
+    value = world * n * args.steps / secs_max / 1e9
+    ms_per_step = secs_max / args.steps * 1e3
+    kernel_s = secs / max(1, launches)  # one kernel per step: launch duration == step duration on this rank
+    achieved = ALG_BYTES_PER_SAMPLE * n / kernel_s / 1e9
+
+    # ---- integrity: bits checksum, cross-rank sum (outside the timed region) ----
+    ones = torch.count_nonzero(bits).to(torch.int64)
+    if dist:
+        dist.all_reduce(ones)
+
+    # ---- e2e through the C ABI with HOST buffers (pinned): H2D + kernel + D2H every step ----
+    e2e = None
+    if not args.no_e2e:
+        e2e_frames = frames
+        avail = 0
+        try:
+            for l in open("/proc/meminfo"):
+                if l.startswith("MemAvailable"):
+                    avail = int(l.split()[1]) * 1024
+        except Exception:
+            pass
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        need = 10 * e2e_frames * FFT_LEN * local_world
+        while avail and need * 2 > avail and e2e_frames > 8192:
+            e2e_frames //= 2
+            need //= 2
+        ne = e2e_frames * FFT_LEN
+        h_in = torch.empty(ne, dtype=torch.complex64).pin_memory()
+        h_out = torch.empty(2 * ne, dtype=torch.uint8).pin_memory()
+        h_in.copy_(x[:ne])
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            chain.run_host(h_in.data_ptr(), ne, h_out.data_ptr())   # returns after the D2H of the result
+
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        l2 = ae.launch_count()
+        for _ in range(e_steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        e_secs = max(e0.elapsed_time(e1) / 1e3, wall)
+        barrier()
+        te = torch.tensor([e_secs], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ne * e_steps / float(te.item()) / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 8 * ne,
+               "d2h_bytes_per_step": 2 * ne, "steps": e_steps, "frames_per_step_per_gpu": e2e_frames,
+               "launches_per_step": (ae.launch_count() - l2) // e_steps,
+               "note": "ae_chain_exec_host: pinned host buffers, 64 MiB chunks, 3-stream H2D/kernel/D2H pipeline; PCIe-bound"}
+        # the host path must give the same bits as the device path
+        same = bool(torch.equal(h_out.cuda(), bits[: 2 * ne]))
+        e2e["matches_device_path"] = same
+        del h_in, h_out
+    sampler.stop()
+    clocks = sampler.summary(t_mark0, t_mark1)
+
+    extra = None
+    cpu = None
+    if rank == 0 and world == 1:
+        if not args.no_extras:
+            try:
+                extra = extras(torch, ae, d_in, frames, hbm_peak)
+            except Exception as ex:  # extras never invalidate the headline line
+                extra = {"error": repr(ex)}
+        if not args.no_cpu:
+            threads = os.cpu_count() or 1
+            gs, ms, cf = cpu_chain_rate(10.0, threads)
+            gs1, ms1, cf1 = cpu_chain_rate(3.0, 1)
+            cpu = {"value": gs, "unit": "Gsamples/s", "cores": threads, "kind": "port",
+                   "sample": "%d frames x %d samples, %d host threads, %.1f s; C++ restatement of aether_primitives (not rustfft)" % (cf, FFT_LEN, threads, ms / 1e3),
+                   "single_thread_value": gs1}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "fft1024_fwd_SN -> fir64 -> qpsk_demod (BASELINE headline chain)", "fft_len": FFT_LEN, "ntaps": NTAPS,
+                       "frames_per_gpu": frames, "samples_per_gpu": n, "compat": "reference", "parallelism": "frames sharded, dp%d" % world,
+                       "l2_policy": "inputs larger than L2 (%.1f GiB in, %.1f GiB out per step)" % (8 * n / 2**30, 2 * n / 2**30)},
+            "roofline": {"bound": "hbm", "kernel": "chain_fused_kernel<1024>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "alg_bytes_per_sample": ALG_BYTES_PER_SAMPLE, "kernel_ms": kernel_s * 1e3,
+                         "fp32_TFLOP/s_nominal": FLOP_PER_SAMPLE * n / kernel_s / 1e12},
+            "e2e": e2e, "gpu_launches": launches, "warmup_launches": l_warm, "clocks": clocks,
+            "checksum_ones": int(ones.item()),
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1 << 20, help="frames per GPU (BASELINE: 2^20)")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -330,18 +330,23 @@ int ora_fir(const ocf32* x, size_t n, const ocf32* h, size_t T, ocf32* y, const 
   if (frame_len == 0) frame_len = n ? n : 1;
   for (size_t i = 0; i < n; ++i) {
     const size_t f0 = (i / frame_len) * frame_len;  // first sample of this frame
+    const size_t in_frame = i - f0 + 1;             // taps that see samples of this frame
+    const size_t kmax = T < in_frame ? T : in_frame;
     float ar = 0.0f, ai = 0.0f;
-    for (size_t k = 0; k < T; ++k) {
-      ocf32 s;
-      if (i >= f0 + k) s = x[i - k];
-      else if (state && f0 == 0) {
-        // history index: sample at time (i-k) < 0 -> state[(T-1) + (i-k)]
-        const long long idx = (long long)(T - 1) + (long long)i - (long long)k;
-        if (idx < 0) continue;
-        s = state[idx];
-      } else continue;
+    for (size_t k = 0; k < kmax; ++k) {
+      const ocf32 s = x[i - k];
       ar = ar + (h[k].re * s.re - h[k].im * s.im);
       ai = ai + (h[k].re * s.im + h[k].im * s.re);
+    }
+    if (state && f0 == 0) {
+      for (size_t k = kmax; k < T; ++k) {
+        // sample at time (i-k) < 0 -> state[(T-1) + (i-k)]
+        const long long idx = (long long)(T - 1) + (long long)i - (long long)k;
+        if (idx < 0) break;
+        const ocf32 s = state[idx];
+        ar = ar + (h[k].re * s.re - h[k].im * s.im);
+        ai = ai + (h[k].re * s.im + h[k].im * s.re);
+      }
     }
     y[i].re = ar; y[i].im = ai;
   }

@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library loads, exports every symbol include/aether_b200.h declares, fails loudly
+without a GPU (no CPU fallback), and the product package never touches oracle/."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "aether_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ae_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from aether_primitives_b200 import _lib
+
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) > 80
+    for s in syms:
+        assert hasattr(lib, s), "libaether_b200.so does not export %s" % s
+    # and the Python binding knows each of them
+    assert set(syms) == set(_lib.EXPORTS)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import aether_primitives_b200 as ae
+
+    if ae.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(ae.AeError) as e:
+        ae.init(0)
+    assert e.value.status == ae._lib.AE_ECUDA
+    with pytest.raises(ae.AeError) as e:
+        ae.DeviceVec.zeros(16)
+    assert e.value.status == ae._lib.AE_ECUDA
+    with pytest.raises(ae.AeError):
+        ae.Cfft.with_len(1024)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "aether_primitives_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(base, f), errors="replace").read()
+                assert "liboracle" not in txt and "aether_oracle" not in txt and "tests.oracle" not in txt, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+    mk = open(os.path.join(ROOT, "Makefile")).read()
+    lib_rule = mk[mk.index("$(LIB): $(OBJS)"):].split("\n\n")[0]
+    assert "oracle" not in lib_rule
+
+
+def test_philox_host_entry_point_needs_no_gpu():
+    from aether_primitives_b200 import noise
+
+    assert noise.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+
+
+def test_scale_factor_host_entry_point():
+    import aether_primitives_b200 as ae
+    from tests import oracle as o
+
+    for n in (1, 4, 100, 1024, 2048, 99999):
+        assert ae.Scale.SN.factor(n) == o.scale_factor(o.SCALE_SN, n)
+        assert ae.Scale.N.factor(n) == o.scale_factor(o.SCALE_N, n)
+    assert ae.Scale.X(2.5).factor(7) == 2.5
