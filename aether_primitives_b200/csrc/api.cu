@@ -35,7 +35,8 @@ struct Ctx {
   int sm_count = 148;
   int* d_err = nullptr;
   std::vector<ae_vec*> pending;               // vecs with a non-empty tape
-  std::map<size_t, float2*> tw_cache;         // twiddle tables by length
+  std::map<size_t, float2*> tw_cache;         // plain twiddle tables W[k] by length (any-length path)
+  std::map<size_t, float2*> ttw_cache;        // per-thread twiddle tables of the power-of-two kernels
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
 };
 
@@ -121,6 +122,21 @@ ae_status get_twiddles(Ctx* c, size_t n, float2** out) {
   CK(cudaMemcpyAsync(p, h.data(), n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->tw_cache[n] = (float2*)p;
+  *out = (float2*)p;
+  return AE_OK;
+}
+
+ae_status get_thread_twiddles(Ctx* c, size_t n, float2** out) {
+  auto it = c->ttw_cache.find(n);
+  if (it != c->ttw_cache.end()) { *out = it->second; return AE_OK; }
+  std::vector<float2> h;
+  fft_thread_twiddles(n, h);
+  if (h.empty()) return fail(AE_EARG, "no power-of-two kernel for this length");
+  void* p = nullptr;
+  TRY(dev_alloc(c, h.size() * sizeof(float2), &p));
+  CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->ttw_cache[n] = (float2*)p;
   *out = (float2*)p;
   return AE_OK;
 }
@@ -631,7 +647,7 @@ ae_status ae_fft_create(size_t len, ae_fft** out) {
   f->c = c; f->len = len; f->compat = AE_COMPAT_REFERENCE;
   f->pow2 = fft_pow2_supported(len);
   f->scratch = nullptr; f->scratch_elems = 0; f->tmp = nullptr; f->tmp_elems = 0;
-  ae_status st = get_twiddles(c, len, &f->tw);
+  ae_status st = f->pow2 ? get_thread_twiddles(c, len, &f->tw) : get_twiddles(c, len, &f->tw);
   if (st != AE_OK) { delete f; return st; }
   if (!f->pow2) {
     size_t m = len;
@@ -764,7 +780,7 @@ ae_status ae_fir_create(const ae_cf32* taps_host, size_t ntaps, int mode, ae_fir
   CK(cudaMemsetAsync(f->d_hist, 0, f->tp * sizeof(float2), c->stream));
   CK(cudaMemsetAsync(f->d_hist2, 0, f->tp * sizeof(float2), c->stream));
   if (mode == AE_FIR_OVERLAP_SAVE) {
-    TRY(get_twiddles(c, nfft, &f->d_tw));
+    TRY(get_thread_twiddles(c, nfft, &f->d_tw));
     std::vector<float2> hp(nfft, make_float2(0.f, 0.f));
     for (size_t i = 0; i < ntaps; ++i) hp[i] = h[i];
     TRY(dev_alloc(c, nfft * sizeof(float2), &p)); f->d_H = (float2*)p;
@@ -904,6 +920,8 @@ ae_status ae_mod_create(const ae_cf32* table, size_t table_len, ae_mod** out) {
   m->c = c;
   m->tab.len = (int)table_len;
   for (size_t i = 0; i < 4; ++i) m->tab.t[i] = i < table_len ? make_float2(table[i].re, table[i].im) : make_float2(0.f, 0.f);
+  m->tab.generic_qpsk = table_len == 4 && table[0].re == 1.f && table[0].im == 1.f && table[1].re == -1.f && table[1].im == 1.f &&
+                        table[2].re == 1.f && table[2].im == -1.f && table[3].re == -1.f && table[3].im == -1.f;
   *out = m;
   return AE_OK;
 }
@@ -1182,7 +1200,7 @@ ae_status ae_chain_create(size_t fft_len, const ae_cf32* taps_host, size_t ntaps
   if (st == AE_OK) st = ae_mod_qpsk(&ch->qpsk);
   if (st != AE_OK) { ae_chain_destroy(ch); return st; }
   if (ch->fused) {
-    TRY(get_twiddles(c, fft_len, &ch->d_tw));
+    TRY(get_thread_twiddles(c, fft_len, &ch->d_tw));
     // window[m] = s * sum_k h[k] exp(-sgn 2 pi i m k / N), sgn = exponent sign of Cfft::fwd
     const double sgn = (compat == AE_COMPAT_REFERENCE) ? +1.0 : -1.0;
     std::vector<float2> w(fft_len), h(ntaps);
@@ -1301,7 +1319,7 @@ ae_status ae_ofdm_chain(size_t fft_len, size_t frames, uint64_t first_frame_id, 
   Ctx* c;
   TRY(get_ctx(&c));
   float2* tw;
-  TRY(get_twiddles(c, fft_len, &tw));
+  TRY(get_thread_twiddles(c, fft_len, &tw));
   const size_t nbits = 2 * fft_len * frames;
   if (tx_bits) { TRY(bits_reserve(tx_bits, nbits)); tx_bits->len = nbits; }
   if (rx_bits) { TRY(bits_reserve(rx_bits, nbits)); rx_bits->len = nbits; }

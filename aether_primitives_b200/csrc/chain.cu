@@ -32,19 +32,21 @@ chain_fused_kernel(const float2* __restrict__ x, uint8_t* __restrict__ bits, siz
   using C = FftCfg<N>;
   using LC = ChainLaunch<N>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [taps: ntaps][per frame: fft buffer A | fft buffer B | tail: ntaps]
+  // layout: [taps: ntaps][per frame: fft buffer A | fft buffer B | rt: ntaps | fix: ntaps]
   float2* hs = reinterpret_cast<float2*>(smem_raw);
   const int f = threadIdx.x / C::T;
   const int t = threadIdx.x % C::T;
-  float2* smA = hs + ntaps + (size_t)f * (2 * C::SMEM_ELEMS + ntaps);
+  float2* smA = hs + ntaps + (size_t)f * (2 * C::SMEM_ELEMS + 2 * ntaps);
   float2* smB = smA + C::SMEM_ELEMS;
-  float2* tail = smB + C::SMEM_ELEMS;  // tail[i] = scale * A[N - (ntaps-1) + i]
+  float2* rt = smB + C::SMEM_ELEMS;
+  float2* fix = rt + ntaps;
   for (int i = threadIdx.x; i < ntaps; i += LC::THREADS) hs[i] = __ldg(taps + i);
   __syncthreads();
-  const size_t frame = (size_t)blockIdx.x * LC::F + f;
-  if (frame >= frames) return;
-  const float2* src = x + frame * N;
   const int tm1 = ntaps - 1;
+  // persistent: every frame slot (C::T threads) walks its own frames and only ever synchronises
+  // with itself, so the slots of an SM drift out of phase and overlap their load / compute phases
+  for (size_t frame = (size_t)blockIdx.x * LC::F + f; frame < frames; frame += (size_t)gridDim.x * LC::F) {
+  const float2* src = x + frame * N;
 
   // ab[0] = x (-> A = DFT(x)), ab[1] = x .* w (-> B = circular convolution of scale*X with h);
   // both transforms advance pass by pass together: twiddles loaded once, barriers shared
@@ -56,30 +58,45 @@ chain_fused_kernel(const float2* __restrict__ x, uint8_t* __restrict__ bits, siz
   float2* const sm2[2] = {smA, smB};
   fft_frames<N, INV, 2>(ab, sm2, tw, t, f);
 
-  // only the last T-1 bins of A are needed (scaled like Cfft::fwd's output)
+  // only the last T-1 bins of A are needed (scaled like Cfft::fwd's output); stored REVERSED:
+  // rt[i] = scale * A[N-1-i], so the fix-up reads rt[i] as a broadcast and the taps contiguously
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
     const int pos = t + m * C::T;
-    if (pos >= N - tm1) tail[pos - (N - tm1)] = cx_scale_exact(ab[0][m], scale);
+    if (pos >= N - tm1) rt[N - 1 - pos] = cx_scale_exact(ab[0][m], scale);
   }
   frame_sync<C::T>(f);
+  // wrap-around terms of the circular convolution, outputs n < T-1:
+  //   fix[n] = sum_{k=n+1}^{T-1} h[k] A[N+n-k] = sum_{i < T-1-n} h[n+1+i] rt[i]
+  // output n belongs to thread n mod C::T, which is also the thread that consumes it below
+  for (int n = t; n < tm1; n += C::T) {
+    float2 acc0 = make_float2(0.0f, 0.0f), acc1 = acc0;
+    const int len = tm1 - n;
+    const float2* hp = hs + n + 1;
+    int i = 0;
+    if ((reinterpret_cast<uintptr_t>(rt) & 15) == 0) {  // one 16-byte broadcast read feeds two taps
+      for (; i + 1 < len; i += 2) {
+        const float4 r2 = *reinterpret_cast<const float4*>(rt + i);
+        cx_fma(acc0, hp[i], make_float2(r2.x, r2.y));
+        cx_fma(acc1, hp[i + 1], make_float2(r2.z, r2.w));
+      }
+    }
+    for (; i < len; ++i) cx_fma(acc0, hp[i], rt[i]);
+    fix[n] = cx_add(acc0, acc1);
+  }
 
-  const float2 tab[4] = {make_float2(1.0f, 1.0f), make_float2(-1.0f, 1.0f), make_float2(1.0f, -1.0f), make_float2(-1.0f, -1.0f)};
   uint8_t* out = bits + 2 * frame * (size_t)N;
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
     const int n = t + m * C::T;
     float2 yv = ab[1][m];
-    if (n < tm1) {  // wrap-around terms of the circular convolution
-      float2 acc = make_float2(0.0f, 0.0f);
-      for (int k = n + 1; k <= tm1; ++k) cx_fma(acc, hs[k], tail[n - k + tm1]);
-      yv = cx_sub(yv, acc);
-    }
-    const unsigned idx = demod_index<4>(yv, tab);  // src/modulation.rs:33-56
+    if (n < tm1) yv = cx_sub(yv, fix[n]);
+    const unsigned idx = demod_qpsk_generic(yv);  // src/modulation.rs:33-56, exact
     const unsigned b0 = idx & 1u;
     const unsigned b1 = compat == AE_COMPAT_REFERENCE ? (idx & 2u) : ((idx >> 1) & 1u);
     *reinterpret_cast<uchar2*>(out + 2 * n) = make_uchar2((unsigned char)b0, (unsigned char)b1);
   }
+  }  // frame loop
 }
 
 bool chain_fused_supported(size_t nfft, size_t ntaps) {
@@ -90,15 +107,20 @@ template <int N>
 static void launch_chain_n(const float2* x, uint8_t* bits, size_t frames, const float2* window, const float2* taps,
                            size_t ntaps, const float2* tw, bool inverse, float scale, int compat, cudaStream_t st) {
   using LC = ChainLaunch<N>;
-  const size_t smem = (ntaps + (size_t)LC::F * (2 * FftCfg<N>::SMEM_ELEMS + ntaps)) * sizeof(float2);
-  const unsigned grid = (unsigned)((frames + LC::F - 1) / LC::F);
-  if (inverse) {
-    cudaFuncSetAttribute(chain_fused_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    chain_fused_kernel<N, true><<<grid, LC::THREADS, smem, st>>>(x, bits, frames, window, taps, (int)ntaps, tw, scale, compat);
-  } else {
-    cudaFuncSetAttribute(chain_fused_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    chain_fused_kernel<N, false><<<grid, LC::THREADS, smem, st>>>(x, bits, frames, window, taps, (int)ntaps, tw, scale, compat);
-  }
+  const size_t smem = (ntaps + (size_t)LC::F * (2 * FftCfg<N>::SMEM_ELEMS + 2 * ntaps)) * sizeof(float2);
+  const size_t want = (frames + LC::F - 1) / LC::F;
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, smem);
+    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);  // grid = SM count x resident CTAs
+    const unsigned grid = (unsigned)(want < resident ? want : resident);
+    kern<<<grid, LC::THREADS, smem, st>>>(x, bits, frames, window, taps, (int)ntaps, tw, scale, compat);
+  };
+  if (inverse) launch(chain_fused_kernel<N, true>);
+  else launch(chain_fused_kernel<N, false>);
 }
 
 void launch_chain_fused(const float2* x, uint8_t* bits, size_t nfft, size_t frames, const float2* window, const float2* taps,
@@ -235,7 +257,7 @@ ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int tw
   for (int m = 0; m < 16; ++m) {
     const float2 y = cx_scale_exact(v[m], sn);
     const unsigned two = (txb >> (2 * m)) & 3u;
-    const unsigned idx = demod_index<4>(y, tab);
+    const unsigned idx = demod_qpsk_generic(y);
     errs += __popc((idx ^ two) & 3u);
     const float dr = y.x - tab[two].x, di = y.y - tab[two].y;
     e_pow += dr * dr + di * di;

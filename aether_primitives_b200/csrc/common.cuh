@@ -75,6 +75,26 @@ __device__ __forceinline__ unsigned demod_index(float2 s, const float2 (&tab)[M]
   return best;
 }
 
+// Hard decision for the GENERIC QPSK table (+-1, +-1) (src/modulation.rs:87-92), bit-identical to
+// demod_index<4> but ~3x cheaper.  With A(+-) = fl(fl(re -+ 1)^2), B(+-) likewise, the reference
+// compares d = fl(A + B).  Rounding is monotone, so the sign-based index is the reference's answer
+// unless two candidates TIE after rounding.  A tie on the re decision needs
+//     4|re| - 6.2u (|re|+1)^2  <=  2.01 u ((|re|+1)^2 + (|im|+1)^2),   u = 2^-24,
+// which cannot happen when |re| > 2^-21 (1 + max(|re|,|im|))^2 (2x margin); same for im.  NaN, inf
+// and the rare near-axis symbols fail the test (comparisons with NaN are false) and take the
+// exact path, so ties ("first minimum wins") and NaN ("later index wins") are reproduced.
+static __device__ __noinline__ unsigned demod_qpsk_exact_slow(float2 s) {  // one out-of-line copy: rare path
+  const float2 tab[4] = {make_float2(1.0f, 1.0f), make_float2(-1.0f, 1.0f), make_float2(1.0f, -1.0f), make_float2(-1.0f, -1.0f)};
+  return demod_index<4>(s, tab);
+}
+__device__ __forceinline__ unsigned demod_qpsk_generic(float2 s) {
+  const float ax = fabsf(s.x), ay = fabsf(s.y);
+  const float u = fmaf(fmaxf(ax, ay), 6.9053396600248786e-4f, 6.9053396600248786e-4f);  // 2^-10.5 (1 + max)
+  const float thr = u * u;
+  if (ax > thr && ay > thr) return (__float_as_uint(s.x) >> 31) | ((__float_as_uint(s.y) >> 31) << 1);
+  return demod_qpsk_exact_slow(s);
+}
+
 // Philox4x32-10 (Salmon et al., Random123).  Known-answer vectors in tests/test_noise.py.
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                        uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {

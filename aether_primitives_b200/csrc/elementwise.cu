@@ -286,8 +286,8 @@ void launch_modulate(const ModTable& tab, const uint8_t* bits, size_t, float2* o
 // idx&1 then idx&2 in {0,2}; compat=corrected emits (idx>>1)&1.
 // =================================================================================================
 template <int M>
-__device__ __forceinline__ void demod_emit(float2 s, const float2 (&tab)[M], int compat, uint8_t* o) {
-  const unsigned idx = demod_index<M>(s, tab);
+__device__ __forceinline__ void demod_emit(float2 s, const float2 (&tab)[M], int compat, uint8_t* o, bool generic = false) {
+  const unsigned idx = (M == 4 && generic) ? demod_qpsk_generic(s) : demod_index<M>(s, tab);
   o[0] = (uint8_t)(idx & 1u);
   if (M == 4) o[1] = compat == AE_COMPAT_REFERENCE ? (uint8_t)(idx & 2u) : (uint8_t)((idx >> 1) & 1u);
 }
@@ -298,20 +298,21 @@ __global__ void __launch_bounds__(256) demod_kernel(const __grid_constant__ ModT
   float2 tab[M];
 #pragma unroll
   for (int c = 0; c < M; ++c) tab[c] = tabp.t[c];
+  const bool generic = tabp.generic_qpsk != 0;
   const size_t s0 = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
   if (s0 >= n) return;
   if (vec_ok && s0 + 4 <= n) {
     const float4 a = __ldcs(reinterpret_cast<const float4*>(sym + s0));
     const float4 b = __ldcs(reinterpret_cast<const float4*>(sym + s0) + 1);
     uint8_t o[4 * BPS];
-    demod_emit<M>(make_float2(a.x, a.y), tab, compat, o);
-    demod_emit<M>(make_float2(a.z, a.w), tab, compat, o + BPS);
-    demod_emit<M>(make_float2(b.x, b.y), tab, compat, o + 2 * BPS);
-    demod_emit<M>(make_float2(b.z, b.w), tab, compat, o + 3 * BPS);
+    demod_emit<M>(make_float2(a.x, a.y), tab, compat, o, generic);
+    demod_emit<M>(make_float2(a.z, a.w), tab, compat, o + BPS, generic);
+    demod_emit<M>(make_float2(b.x, b.y), tab, compat, o + 2 * BPS, generic);
+    demod_emit<M>(make_float2(b.z, b.w), tab, compat, o + 3 * BPS, generic);
     if (BPS == 2) __stcs(reinterpret_cast<uint2*>(bits + s0 * 2), *reinterpret_cast<uint2*>(o));
     else __stcs(reinterpret_cast<uint32_t*>(bits + s0), *reinterpret_cast<uint32_t*>(o));
   } else {
-    for (size_t s = s0; s < n && s < s0 + 4; ++s) demod_emit<M>(sym[s], tab, compat, bits + s * BPS);
+    for (size_t s = s0; s < n && s < s0 + 4; ++s) demod_emit<M>(sym[s], tab, compat, bits + s * BPS, generic);
   }
 }
 void launch_demod(const ModTable& tab, const float2* sym, size_t n, uint8_t* bits, int compat, cudaStream_t st) {
@@ -396,6 +397,7 @@ __global__ void __launch_bounds__(256) modem_kernel(const __grid_constant__ ModT
   float2 tab[M];
 #pragma unroll
   for (int c = 0; c < M; ++c) tab[c] = tabp.t[c];
+  const bool generic = tabp.generic_qpsk != 0;
   unsigned long long errs = 0;
   // pairs are aligned to the GLOBAL sample index so the stream does not depend on `offset` parity
   const uint64_t p0 = offset >> 1;
@@ -433,7 +435,7 @@ __global__ void __launch_bounds__(256) modem_kernel(const __grid_constant__ ModT
       float2 nz = cx_scale_exact(z[i], scale);
       if (twice) nz = cx_scale_exact(nz, scale);
       s = cx_add_exact(s, nz);
-      demod_emit<M>(s, tab, compat, bo + i * BPS);
+      demod_emit<M>(s, tab, compat, bo + i * BPS, generic);
       if (ok) {
 #pragma unroll
         for (int b = 0; b < BPS; ++b) errs += ((bi[i * BPS + b] != 0) != (bo[i * BPS + b] != 0));

@@ -2,6 +2,9 @@
 // Replaces rustfft under fft::Cfft (src/fft.rs:134-235).  Scale::{SN,N,X} (src/fft.rs:22-37) is
 // folded into the last pass as one separately rounded multiply, which reproduces the
 // reference's "transform, then vec_scale" rounding sequence on this kernel's own output.
+#include <cmath>
+#include <vector>
+
 #include "fft_device.cuh"
 #include "internal.h"
 
@@ -30,39 +33,83 @@ fft_pow2_kernel(const float2* __restrict__ in, float2* __restrict__ out, const f
   float2* smem = reinterpret_cast<float2*>(smem_raw);
   const int f = threadIdx.x / C::T;
   const int t = threadIdx.x % C::T;
-  const size_t frame = (size_t)blockIdx.x * LC::F + f;
-  if (frame >= frames) return;  // whole frame groups leave together (barriers are per frame)
-  const float2* src = in + frame * N;
-  float2 x[16];
+  // persistent: each frame slot (C::T threads) walks its own frames and synchronises only with
+  // itself, so the slots resident on an SM drift apart and overlap their load / compute / store phases
+  for (size_t frame = (size_t)blockIdx.x * LC::F + f; frame < frames; frame += (size_t)gridDim.x * LC::F) {
+    const float2* src = in + frame * N;
+    float2 x[16];
 #pragma unroll
-  for (int m = 0; m < 16; ++m) x[m] = ld_stream(src + t + m * C::T);
-  fft_frame<N, INV>(x, smem + f * C::SMEM_ELEMS, tw, t, f);
-  float2* dst = out + frame * N;
-  if (do_scale) {
+    for (int m = 0; m < 16; ++m) x[m] = ld_stream(src + t + m * C::T);
+    fft_frame<N, INV>(x, smem + f * C::SMEM_ELEMS, tw, t, f);
+    float2* dst = out + frame * N;
+    if (do_scale) {
 #pragma unroll
-    for (int m = 0; m < 16; ++m) x[m] = cx_scale_exact(x[m], scale);
+      for (int m = 0; m < 16; ++m) x[m] = cx_scale_exact(x[m], scale);
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) st_stream(dst + t + m * C::T, x[m]);
+    // the next frame's first pass stores into the same shared frame: everyone must be past its reads
+    if (C::NP > 1) frame_sync<C::T>(f);
   }
-#pragma unroll
-  for (int m = 0; m < 16; ++m) st_stream(dst + t + m * C::T, x[m]);
 }
 
 template <int N>
 static void launch_pow2_n(const float2* in, float2* out, size_t frames, const float2* tw, bool inverse, bool do_scale,
                           float scale, cudaStream_t st) {
   using LC = FftLaunch<N>;
-  const unsigned grid = (unsigned)((frames + LC::F - 1) / LC::F);
-  if (inverse) {
-    if (LC::SMEM > 48 * 1024)
-      cudaFuncSetAttribute(fft_pow2_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
-    fft_pow2_kernel<N, true><<<grid, LC::THREADS, LC::SMEM, st>>>(in, out, tw, frames, scale, do_scale);
-  } else {
-    if (LC::SMEM > 48 * 1024)
-      cudaFuncSetAttribute(fft_pow2_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
-    fft_pow2_kernel<N, false><<<grid, LC::THREADS, LC::SMEM, st>>>(in, out, tw, frames, scale, do_scale);
-  }
+  const size_t want = (frames + LC::F - 1) / LC::F;
+  auto launch = [&](auto kern) {
+    if (LC::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
+    static int resident = 0;  // SM count x resident CTAs per SM, queried once per kernel instantiation
+    if (!resident) {
+      int per_sm = 1, dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, LC::SMEM);
+      resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const unsigned grid = (unsigned)(want < (size_t)resident ? want : (size_t)resident);
+    kern<<<grid, LC::THREADS, LC::SMEM, st>>>(in, out, tw, frames, scale, do_scale);
+  };
+  if (inverse) launch(fft_pow2_kernel<N, true>);
+  else launch(fft_pow2_kernel<N, false>);
 }
 
 bool fft_pow2_supported(size_t n) { return n >= 16 && n <= 16384 && (n & (n - 1)) == 0; }
+
+// Per-thread twiddle table of the power-of-two kernels (layout described in fft_device.cuh):
+// for every pass p >= 1 and thread t the handful of exp(-2 pi i e/n) values that thread needs,
+// evaluated in f64 and rounded to f32.
+template <int N>
+static void thread_twiddles_n(std::vector<float2>& out) {
+  using C = FftCfg<N>;
+  out.assign((size_t)(C::TW_ROWS > 0 ? C::TW_ROWS : 1) * C::T, make_float2(1.f, 0.f));
+  auto W = [](long long e) {
+    const double a = -2.0 * 3.14159265358979323846 * (double)(e % N) / (double)N;
+    return make_float2((float)std::cos(a), (float)std::sin(a));
+  };
+  for (int p = 1; p < C::NP; ++p) {
+    const int R = C::radix(p), NS = C::ns(p), row0 = C::tw_row0(p);
+    for (int t = 0; t < C::T; ++t) {
+      if (R == 16) {
+        const long long u = (long long)(t & (NS - 1)) * (N / (NS * 16));
+        const int mult[6] = {1, 2, 3, 4, 8, 12};
+        for (int e = 0; e < 6; ++e) out[(size_t)(row0 + e) * C::T + t] = W(mult[e] * u);
+      } else {
+        for (int r = 1; r < R; ++r) out[(size_t)(row0 + r - 1) * C::T + t] = W((long long)r * t);
+      }
+    }
+  }
+}
+void fft_thread_twiddles(size_t n, std::vector<float2>& out) {
+  switch (n) {
+#define AE_CASE(NN) case NN: thread_twiddles_n<NN>(out); break;
+    AE_CASE(16) AE_CASE(32) AE_CASE(64) AE_CASE(128) AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048)
+    AE_CASE(4096) AE_CASE(8192) AE_CASE(16384)
+#undef AE_CASE
+    default: out.clear();
+  }
+}
 
 void launch_fft_pow2(const float2* in, float2* out, size_t n, size_t frames, const float2* tw, bool inverse, bool do_scale,
                      float scale, cudaStream_t st) {

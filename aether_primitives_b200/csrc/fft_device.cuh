@@ -18,9 +18,10 @@
 // stride-16 stores of the first pass are bank-conflict free); the last pass leaves them in
 // registers.
 //
-// Twiddles come from a table tw[k] = exp(-2 pi i k/N) computed in f64 on the host and rounded to
-// f32 (rustfft's accuracy class).  Table reads are scattered 8-byte loads that cost L1 wavefronts,
-// and the first profile of the fused chain showed the LSU data pipe at 81 % because of them, so
+// Twiddles exp(-2 pi i k/N) are computed in f64 on the host and rounded to f32 (rustfft's accuracy
+// class).  Reading a plain table W[k] costs scattered 8-byte loads, and the first profile of the
+// fused chain showed the L1 data pipe at 81 % because of them, so the host re-lays the values out
+// PER THREAD (`tw` below is that table: row-major [row][t], coalesced, L1-resident) and
 //   * a radix-16 pass loads only W^1,W^2,W^3 and W^4,W^8,W^12 and forms W^(4a+b) = W^(4a) W^b;
 //   * the last (radix-2^REM) pass has k = t + q*T, so W^(r k) = W^(r t) * W16^(r q): R-1 loads,
 //     the rest are compile-time constants;
@@ -45,6 +46,11 @@ struct FftCfg {
   static_assert(N >= 16 && (N & (N - 1)) == 0, "power of two >= 16");
   static constexpr int radix(int p) { return p < A ? 16 : (1 << REM); }
   static constexpr int ns(int p) { return 1 << (4 * p); }  // 16^p
+  // per-thread twiddle table (built on the host, see fft_thread_twiddles): pass p >= 1 owns
+  // tw_entries(p) rows of T values each, row-major [row][t] so a warp reads contiguous cf32
+  static constexpr int tw_entries(int p) { return p == 0 ? 0 : (radix(p) == 16 ? 6 : radix(p) - 1); }
+  static constexpr int tw_row0(int p) { return p <= 1 ? 0 : tw_row0(p - 1) + tw_entries(p - 1); }
+  static constexpr int TW_ROWS = tw_row0(NP - 1) + tw_entries(NP - 1);
 };
 
 __device__ __forceinline__ int fft_pad(int i) { return i + (i >> 4); }
@@ -177,16 +183,18 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[NB][16], float2* const (&sm
   constexpr int TWS = N / (NS * R);
   if constexpr (R == 16) {
     const int k = t & (NS - 1);
+    (void)TWS;
     float2 v[NB][16];
 #pragma unroll
     for (int b = 0; b < NB; ++b)
 #pragma unroll
       for (int r = 0; r < 16; ++r) v[b][r] = x[b][r];
     if constexpr (NS > 1) {
-      const int u = k * TWS;
+      // rows: W^u, W^2u, W^3u, W^4u, W^8u, W^12u with u = (t mod NS) * TWS, one value per thread
+      const float2* row = tw + C::tw_row0(P) * T + t;
       float2 wl[4], wh[4];  // W^b (b = 1..3) and W^(4a) (a = 1..3)
 #pragma unroll
-      for (int i = 1; i < 4; ++i) { wl[i] = __ldg(tw + i * u); wh[i] = __ldg(tw + 4 * i * u); }
+      for (int i = 1; i < 4; ++i) { wl[i] = __ldg(row + (i - 1) * T); wh[i] = __ldg(row + (i + 2) * T); }
 #pragma unroll
       for (int r = 1; r < 16; ++r) {
         const int a = r >> 2, bb = r & 3;
@@ -219,9 +227,10 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[NB][16], float2* const (&sm
   } else {
     // last pass, radix R < 16, B = 16/R butterflies per thread; k = j = t + q*T, TWS == 1
     static_assert(LAST && TWS == 1, "sub-radix pass must be the last one");
-    float2 wt[R];  // W^(r t)
+    float2 wt[R];  // W^(r t), rows r = 1..R-1 of this pass
+    const float2* row = tw + C::tw_row0(P) * T + t;
 #pragma unroll
-    for (int r = 1; r < R; ++r) wt[r] = __ldg(tw + r * t);
+    for (int r = 1; r < R; ++r) wt[r] = __ldg(row + (r - 1) * T);
     static_for<0, B>([&](auto qc) {
       constexpr int q = decltype(qc)::value;
 #pragma unroll

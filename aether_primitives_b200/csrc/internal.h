@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <vector>
 #include "../../include/aether_b200.h"
 
 namespace ae {
@@ -28,7 +29,7 @@ void launch_downsample_u8(const uint8_t* src, uint8_t* dst, size_t n_dst, size_t
 void launch_interpolate(const float2* src, size_t n_src, float2* dst, size_t n_between, int compat, cudaStream_t st);
 
 // ---- K7/K8 modulation ------------------------------------------------------------------------
-struct ModTable { float2 t[4]; int len; };
+struct ModTable { float2 t[4]; int len; int generic_qpsk; };
 void launch_modulate(const ModTable& tab, const uint8_t* bits, size_t nbits, float2* out, size_t n_out,
                      int* errflag, cudaStream_t st);
 void launch_demod(const ModTable& tab, const float2* sym, size_t n, uint8_t* bits, int compat, cudaStream_t st);
@@ -52,15 +53,16 @@ void launch_bit_errors(const uint8_t* a, const uint8_t* b, size_t n, ae_stats* s
 void launch_evm_acc(const float2* act, const float2* ref, size_t n, ae_stats* stats, int sm_count, cudaStream_t st);
 
 // ---- K2 FFT ----------------------------------------------------------------------------------
-// power-of-two register/shared-memory kernel, 16 <= n <= 16384.  tw[k] = exp(-2 pi i k/n).
+// power-of-two register/shared-memory kernel, 16 <= n <= 16384.  `tw` of every power-of-two launcher
+// below (FFT, overlap-save FIR, chains) is the PER-THREAD table built by fft_thread_twiddles().
 bool fft_pow2_supported(size_t n);
+void fft_thread_twiddles(size_t n, std::vector<float2>& out);
 void launch_fft_pow2(const float2* in, float2* out, size_t n, size_t frames, const float2* tw, bool inverse,
                      bool do_scale, float scale, cudaStream_t st);
 // any length: one global-memory Stockham pass per prime-power factor; needs 2 scratch buffers
 void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n, size_t frames, const float2* tw,
                         const uint32_t* radices, int n_radices, bool inverse, bool do_scale, float scale,
                         cudaStream_t st);
-int fft_launches_pow2();
 // ---- K3/K4 FIR -------------------------------------------------------------------------------
 void launch_fir_direct(const float2* x, float2* y, size_t n, const float2* taps_padded, int ntaps_padded,
                        const float2* history /*ntaps_padded-1 samples or null*/, size_t frame_len, int sm_count,
