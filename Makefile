@@ -32,3 +32,11 @@ clean:
 	rm -rf build $(LIB) $(ORACLE)
 
 .PHONY: all clean oracle lib
+
+# C++ host-mirror test (links the C-ABI library only; run it on a GPU box)
+CPPTEST := build/host_mirror_test
+$(CPPTEST): tests/cpp/host_mirror_test.cpp include/aether_b200.hpp include/aether_b200.h $(LIB)
+	@mkdir -p build
+	$(CXX) -std=c++17 -O2 -Iinclude $< -o $@ -L$(LIBDIR) -laether_b200 -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+cpptest: $(CPPTEST)
+.PHONY: cpptest

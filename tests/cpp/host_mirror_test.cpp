@@ -1,0 +1,110 @@
+// C++ host-mirror test: the reference crate's own unit tests and doctests for the hot path,
+// re-stated against aether_b200.hpp (each block cites the Rust test it mirrors).  Exit code 0 = pass.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "aether_b200.hpp"
+
+using namespace aether;
+
+// assert_evm! (src/lib.rs:26-49), literal formula
+static void assert_evm(const std::vector<cf32>& act, const std::vector<cf32>& ref, double db, const char* what) {
+  if (act.size() != ref.size()) { std::printf("FAIL %s: Input slices/vectors must be same length\n", what); std::exit(1); }
+  const float thr = (float)std::pow(10.0, db / 10.0);
+  for (size_t i = 0; i < act.size(); ++i) {
+    const float evm = std::abs(act[i] - ref[i]);
+    const float limit = std::abs(ref[i]) * thr;
+    if (evm > limit) { std::printf("FAIL %s: EVM limit exceeded at element %zu: %g > %g\n", what, i, evm, limit); std::exit(1); }
+  }
+}
+static std::vector<cf32> rep(cf32 v, size_t n) { return std::vector<cf32>(n, v); }
+#define EXPECT_PANIC(stmt, st, what)                                                     \
+  do {                                                                                   \
+    bool ok__ = false;                                                                   \
+    try { stmt; } catch (const Panic& p) { ok__ = (p.status == (st)); }                  \
+    if (!ok__) { std::printf("FAIL %s: expected panic\n", what); std::exit(1); }         \
+  } while (0)
+
+int main() {
+  init(0);
+  {  // src/vecops.rs:340-424
+    DeviceVec v(rep({0.5f, 0.5f}, 100));
+    assert_evm(v.vec_scale(2.0f).to_host(), rep({1, 1}, 100), -80, "vec_scale");
+    DeviceVec ones(rep({1, 1}, 100)), twos(rep({0, 2}, 100));
+    assert_evm(ones.vec_mul(twos).to_host(), rep({-2, 2}, 100), -80, "vec_mul");
+    DeviceVec a(rep({2, 2}, 100)), b(rep({2, 0}, 100));
+    assert_evm(a.vec_div(b).to_host(), rep({1, 1}, 100), -80, "vec_div");
+    DeviceVec c(rep({1, 1}, 100));
+    assert_evm(c.vec_conj().to_host(), rep({1, -1}, 100), -80, "vec_conj");
+    DeviceVec even(std::vector<cf32>{{0, 0}, {1, 0}, {2, 0}, {3, 0}});
+    assert_evm(even.vec_mirror().to_host(), {{2, 0}, {3, 0}, {0, 0}, {1, 0}}, -80, "vec_mirror");
+    DeviceVec short_v(4);
+    EXPECT_PANIC(c.vec_add(short_v), AE_ELEN, "Vectors must have same length");
+  }
+  {  // VecOps doctest src/vecops.rs:19-36
+    DeviceVec v(rep({2, 2}, 100)), twos(rep({2, 2}, 100)), ones(rep({1, 1}, 100));
+    v.vec_div(twos).vec_mul(twos).vec_zero().vec_add(ones).vec_sub(twos).vec_clone(ones)
+        .vec_mutate([](cf32& z) { z.imag(-1.0f); }).vec_conj().vec_mirror();
+    assert_evm(v.to_host(), rep({1, 1}, 100), -80, "vecops doctest chain");
+  }
+  {  // vec_mutate src/vecops.rs:427-441
+    DeviceVec v(rep({1, 1}, 100));
+    int x = 0;
+    v.vec_mutate([&x](cf32& z) { z *= (float)x; ++x; });
+    std::vector<cf32> lin(100);
+    for (int i = 0; i < 100; ++i) lin[i] = {(float)i, (float)i};
+    assert_evm(v.to_host(), lin, -80, "vec_mutate");
+  }
+  {  // fft doctest src/fft.rs:93-117
+    DeviceVec data(rep({1, 0}, 128));
+    data.vec_fft(Scale::None());
+    std::vector<cf32> right(128, {0, 0});
+    right[0] = {128, 0};
+    assert_evm(data.to_host(), right, -80, "fft doctest: DC bin");
+    Cfft f = Cfft::with_len(128);
+    f.ibwd(data, Scale::N());
+    assert_evm(data.to_host(), rep({1, 0}, 128), -80, "fft doctest: ibwd N");
+    data.vec_rfft(f, Scale::SN()).vec_scale(2.0f).vec_rifft(f, Scale::SN());
+    assert_evm(data.to_host(), rep({2, 0}, 128), -72, "fft doctest: rfft*2*rifft");
+    DeviceVec wrong(100);
+    EXPECT_PANIC(f.ifwd(wrong, Scale::None()), AE_ELEN, "Input and FFT must be the same length");
+  }
+  {  // src/modulation.rs:158-196
+    Modulation q = qpsk(), b = bpsk();
+    DeviceBits bits(std::vector<uint8_t>{0, 0, 1, 0, 0, 1, 1, 1});
+    assert_evm(q.modulate(bits).to_host(), {{1, 1}, {-1, 1}, {1, -1}, {-1, -1}}, -80, "generic_qpsk");
+    DeviceBits bb(std::vector<uint8_t>{0, 1, 0, 1});
+    assert_evm(b.modulate(bb).to_host(), {{1, 1}, {-1, -1}, {1, 1}, {-1, -1}}, -80, "generic_bpsk");
+    DeviceBits zeros(std::vector<uint8_t>(100, 0)), out(100);
+    DeviceVec sym = q.modulate(zeros);
+    q.demod_naive(sym, out);
+    if (out.to_host() != std::vector<uint8_t>(100, 0)) { std::printf("FAIL naive_demod\n"); return 1; }
+  }
+  {  // src/sampling.rs:73-169, src/sequence.rs:61-68
+    DeviceVec src(std::vector<cf32>{{0, 0}, {3, 3}, {6, 6}, {9, 9}});
+    DeviceVec dst = DeviceVec::with_capacity(16);
+    sampling::interpolate(src, dst, 2);
+    std::vector<cf32> chk(10);
+    for (int i = 0; i < 10; ++i) chk[i] = {(float)i, (float)i};
+    if (dst.to_host() != chk) { std::printf("FAIL interpolate_2_between\n"); return 1; }
+    DeviceVec s7(7), d3(3);
+    EXPECT_PANIC(sampling::downsample(s7, d3), AE_ELEN, "downsample_7_v_3_fail");
+    if (sequence::generate({1, 0}, {1, 2}, 6).to_host() != std::vector<uint8_t>{1, 0, 1, 1, 0, 1}) { std::printf("FAIL simple_sequence\n"); return 1; }
+  }
+  {  // examples/modem.rs:15-32
+    Modulation m = qpsk();
+    std::vector<uint8_t> b(100);
+    for (int i = 0; i < 100; ++i) b[i] = (uint8_t)((i * 7 + i / 3) & 1);
+    DeviceBits bits(b);
+    DeviceVec sym = m.modulate(bits);
+    Awgn n = noise::new_(0.01f, 815);
+    n.apply(sym);
+    DeviceBits rx(100);
+    m.demod_naive(sym, rx, Compat::Corrected);
+    if (rx.to_host() != b) { std::printf("FAIL modem loop-back\n"); return 1; }
+  }
+  sync();
+  std::printf("host mirror ok\n");
+  return 0;
+}
