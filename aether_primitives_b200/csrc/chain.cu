@@ -13,89 +13,136 @@
 // which needs the last T-1 bins of the plain transform.  So each frame runs two in-register FFTs
 // (A = DFT(x), B = DFT(x .* w)), a triangular fix-up of T(T-1)/2 complex MACs, and the exact
 // reference hard decision on the result:  ~2*50 + 6 + 16 flop/sample instead of 562.
+#include <cstdlib>
+
+#include "async_copy.cuh"
 #include "fft_device.cuh"
 #include "internal.h"
 
 namespace ae {
 
+// frame slots per CTA: 128-thread CTAs (256 when one frame needs them), 4 (2) CTAs per SM
 template <int N>
 struct ChainLaunch {
   static constexpr int T = FftCfg<N>::T;
-  static constexpr int F = T >= 256 ? 1 : (256 / T);
+  static constexpr int F = T >= 128 ? 1 : (128 / T);
   static constexpr int THREADS = F * T;
+  static constexpr int MINB = THREADS <= 128 ? 4 : 2;
 };
+// shared-memory layout (in cf32): [taps, zero padded: HP][per slot: A | B | rt: RP | fix: RP | staging: N if STAGED][mbarriers]
+__host__ __device__ constexpr int chain_hp(int ntaps) { return ((ntaps + 36 + 1) / 2) * 2; }
+__host__ __device__ constexpr int chain_rp(int ntaps) { return ((ntaps + 4 + 1) / 2) * 2; }
+template <int N>
+__host__ __device__ constexpr size_t chain_slot_elems(int ntaps, bool staged) {
+  return 2 * (size_t)FftCfg<N>::SMEM_ELEMS + 2 * (size_t)chain_rp(ntaps) + (staged ? N : 0);
+}
 
-template <int N, bool INV>
-__global__ void __launch_bounds__(ChainLaunch<N>::THREADS)
+// PRUNE : ntaps-1 <= N/16, so the fix-up only needs register 15 (positions >= N - N/16) of A and
+//         transform A is pruned to those bins (fft_device.cuh, TAIL0).
+// STAGED: the next frame's 8N input bytes are fetched by ONE cp.async.bulk (TMA) per frame into the
+//         slot's staging buffer while the current frame is transformed; completion arrives on an
+//         mbarrier.  Needs a 16-byte aligned input; otherwise the plain-load variant runs.
+template <int N, bool INV, bool PRUNE, bool STAGED>
+__global__ void __launch_bounds__(ChainLaunch<N>::THREADS, ChainLaunch<N>::MINB)
 chain_fused_kernel(const float2* __restrict__ x, uint8_t* __restrict__ bits, size_t frames, const float2* __restrict__ window,
                    const float2* __restrict__ taps, int ntaps, const float2* __restrict__ tw, float scale, int compat) {
   using C = FftCfg<N>;
   using LC = ChainLaunch<N>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [taps: ntaps][per frame: fft buffer A | fft buffer B | rt: ntaps | fix: ntaps]
   float2* hs = reinterpret_cast<float2*>(smem_raw);
   const int f = threadIdx.x / C::T;
   const int t = threadIdx.x % C::T;
-  float2* smA = hs + ntaps + (size_t)f * (2 * C::SMEM_ELEMS + 2 * ntaps);
+  const int HP = chain_hp(ntaps), RP = chain_rp(ntaps);
+  const size_t slot = chain_slot_elems<N>(ntaps, STAGED);
+  float2* smA = hs + HP + (size_t)f * slot;
   float2* smB = smA + C::SMEM_ELEMS;
-  float2* rt = smB + C::SMEM_ELEMS;
-  float2* fix = rt + ntaps;
-  for (int i = threadIdx.x; i < ntaps; i += LC::THREADS) hs[i] = __ldg(taps + i);
+  float2* rt = smB + C::SMEM_ELEMS;   // rt[i] = scale * A[N-1-i], zero padded
+  float2* fix = rt + RP;
+  float2* xin = fix + RP;             // STAGED only
+  uint64_t* bar = reinterpret_cast<uint64_t*>(hs + HP + (size_t)LC::F * slot) + f;
+  for (int i = threadIdx.x; i < HP; i += LC::THREADS) hs[i] = i < ntaps ? __ldg(taps + i) : make_float2(0.0f, 0.0f);
+  for (int i = t; i < RP; i += C::T) rt[i] = make_float2(0.0f, 0.0f);
+  const size_t stride = (size_t)gridDim.x * LC::F;
+  size_t frame = (size_t)blockIdx.x * LC::F + f;
+  if (STAGED && t == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    if (frame < frames) {
+      mbar_expect_tx(bar, N * (uint32_t)sizeof(float2));
+      bulk_g2s(xin, x + frame * N, N * (uint32_t)sizeof(float2), bar);
+    }
+  }
   __syncthreads();
   const int tm1 = ntaps - 1;
+  uint32_t phase = 0;
   // persistent: every frame slot (C::T threads) walks its own frames and only ever synchronises
   // with itself, so the slots of an SM drift out of phase and overlap their load / compute phases
-  for (size_t frame = (size_t)blockIdx.x * LC::F + f; frame < frames; frame += (size_t)gridDim.x * LC::F) {
-  const float2* src = x + frame * N;
-
-  // ab[0] = x (-> A = DFT(x)), ab[1] = x .* w (-> B = circular convolution of scale*X with h);
-  // both transforms advance pass by pass together: twiddles loaded once, barriers shared
-  float2 ab[2][16];
+  for (; frame < frames; frame += stride) {
+    // ab[0] = x (-> A = DFT(x)), ab[1] = x .* w (-> B = circular convolution of scale*X with h);
+    // both transforms advance pass by pass together: twiddles loaded once, barriers shared
+    float2 ab[2][16];
+    if (STAGED) {
+      mbar_wait(bar, phase);
+      phase ^= 1u;
 #pragma unroll
-  for (int m = 0; m < 16; ++m) ab[0][m] = ld_stream(src + t + m * C::T);
+      for (int m = 0; m < 16; ++m) ab[0][m] = xin[t + m * C::T];
+    } else {
+      const float2* src = x + frame * N;
 #pragma unroll
-  for (int m = 0; m < 16; ++m) ab[1][m] = cx_mul(ab[0][m], __ldg(window + t + m * C::T));
-  float2* const sm2[2] = {smA, smB};
-  fft_frames<N, INV, 2>(ab, sm2, tw, t, f);
-
-  // only the last T-1 bins of A are needed (scaled like Cfft::fwd's output); stored REVERSED:
-  // rt[i] = scale * A[N-1-i], so the fix-up reads rt[i] as a broadcast and the taps contiguously
-#pragma unroll
-  for (int m = 0; m < 16; ++m) {
-    const int pos = t + m * C::T;
-    if (pos >= N - tm1) rt[N - 1 - pos] = cx_scale_exact(ab[0][m], scale);
-  }
-  frame_sync<C::T>(f);
-  // wrap-around terms of the circular convolution, outputs n < T-1:
-  //   fix[n] = sum_{k=n+1}^{T-1} h[k] A[N+n-k] = sum_{i < T-1-n} h[n+1+i] rt[i]
-  // output n belongs to thread n mod C::T, which is also the thread that consumes it below
-  for (int n = t; n < tm1; n += C::T) {
-    float2 acc0 = make_float2(0.0f, 0.0f), acc1 = acc0;
-    const int len = tm1 - n;
-    const float2* hp = hs + n + 1;
-    int i = 0;
-    if ((reinterpret_cast<uintptr_t>(rt) & 15) == 0) {  // one 16-byte broadcast read feeds two taps
-      for (; i + 1 < len; i += 2) {
-        const float4 r2 = *reinterpret_cast<const float4*>(rt + i);
-        cx_fma(acc0, hp[i], make_float2(r2.x, r2.y));
-        cx_fma(acc1, hp[i + 1], make_float2(r2.z, r2.w));
-      }
+      for (int m = 0; m < 16; ++m) ab[0][m] = ld_stream(src + t + m * C::T);
     }
-    for (; i < len; ++i) cx_fma(acc0, hp[i], rt[i]);
-    fix[n] = cx_add(acc0, acc1);
-  }
-
-  uint8_t* out = bits + 2 * frame * (size_t)N;
 #pragma unroll
-  for (int m = 0; m < 16; ++m) {
-    const int n = t + m * C::T;
-    float2 yv = ab[1][m];
-    if (n < tm1) yv = cx_sub(yv, fix[n]);
-    const unsigned idx = demod_qpsk_generic(yv);  // src/modulation.rs:33-56, exact
-    const unsigned b0 = idx & 1u;
-    const unsigned b1 = compat == AE_COMPAT_REFERENCE ? (idx & 2u) : ((idx >> 1) & 1u);
-    *reinterpret_cast<uchar2*>(out + 2 * n) = make_uchar2((unsigned char)b0, (unsigned char)b1);
-  }
+    for (int m = 0; m < 16; ++m) ab[1][m] = cx_mul(ab[0][m], __ldg(window + t + m * C::T));
+    float2* const sm2[2] = {smA, smB};
+    // after the first slot barrier every thread has consumed its staged inputs: refill the buffer
+    auto prefetch = [&]() {
+      if (STAGED && t == 0 && frame + stride < frames) {
+        mbar_expect_tx(bar, N * (uint32_t)sizeof(float2));
+        bulk_g2s(xin, x + (frame + stride) * N, N * (uint32_t)sizeof(float2), bar);
+      }
+    };
+    fft_frames<N, INV, 2, PRUNE>(ab, sm2, tw, t, f, prefetch);
+
+    // only the last T-1 bins of A are needed (scaled like Cfft::fwd's output); stored REVERSED so the
+    // fix-up reads rt[i] as a broadcast and the taps contiguously
+#pragma unroll
+    for (int m = PRUNE ? 15 : 0; m < 16; ++m) {
+      const int pos = t + m * C::T;
+      if (pos >= N - tm1) rt[N - 1 - pos] = cx_scale_exact(ab[0][m], scale);
+    }
+    frame_sync<C::T>(f);
+    // wrap-around terms of the circular convolution, outputs n < T-1:
+    //   fix[n] = sum_{k=n+1}^{T-1} h[k] A[N+n-k] = sum_{i < T-1-n} h[n+1+i] rt[i]
+    // Taps and rt are zero padded, so every lane of a warp runs the same trip count (the longest
+    // sum of the warp) with no predicates; 4 taps per iteration, rt read as 16-byte broadcasts.
+    // Output n belongs to thread n mod C::T, which is also the thread that consumes it below.
+    for (int n = t; n < tm1; n += C::T) {
+      const int n_first = n - (threadIdx.x & 31);  // first output of this warp
+      const int maxlen = tm1 - (n_first > 0 ? n_first : 0);
+      float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
+      const float2* hp = hs + n + 1;
+      for (int i = 0; i < maxlen; i += 4) {
+        const float4 r01 = *reinterpret_cast<const float4*>(rt + i);
+        const float4 r23 = *reinterpret_cast<const float4*>(rt + i + 2);
+        cx_fma(a0, hp[i], make_float2(r01.x, r01.y));
+        cx_fma(a1, hp[i + 1], make_float2(r01.z, r01.w));
+        cx_fma(a2, hp[i + 2], make_float2(r23.x, r23.y));
+        cx_fma(a3, hp[i + 3], make_float2(r23.z, r23.w));
+      }
+      fix[n] = cx_add(cx_add(a0, a1), cx_add(a2, a3));
+    }
+
+    uint8_t* out = bits + 2 * frame * (size_t)N;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int n = t + m * C::T;
+      float2 yv = ab[1][m];
+      if (n < tm1) yv = cx_sub(yv, fix[n]);
+      const unsigned idx = demod_qpsk_generic(yv);  // src/modulation.rs:33-56, exact
+      const unsigned b0 = idx & 1u;
+      const unsigned b1 = compat == AE_COMPAT_REFERENCE ? (idx & 2u) : ((idx >> 1) & 1u);
+      *reinterpret_cast<uchar2*>(out + 2 * n) = make_uchar2((unsigned char)b0, (unsigned char)b1);
+    }
   }  // frame loop
 }
 
@@ -103,24 +150,38 @@ bool chain_fused_supported(size_t nfft, size_t ntaps) {
   return nfft >= 256 && nfft <= 4096 && (nfft & (nfft - 1)) == 0 && ntaps >= 1 && ntaps <= nfft;
 }
 
+template <int N, bool STAGED, class K>
+static void launch_chain_kernel(K kern, const float2* x, uint8_t* bits, size_t frames, const float2* window, const float2* taps,
+                                size_t ntaps, const float2* tw, float scale, int compat, cudaStream_t st) {
+  using LC = ChainLaunch<N>;
+  const size_t smem = ((size_t)chain_hp((int)ntaps) + (size_t)LC::F * chain_slot_elems<N>((int)ntaps, STAGED)) * sizeof(float2) +
+                      (size_t)LC::F * sizeof(uint64_t);
+  const size_t want = (frames + LC::F - 1) / LC::F;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 1, dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, smem);
+  const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);  // grid = SM count x resident CTAs
+  const unsigned grid = (unsigned)(want < resident ? want : resident);
+  kern<<<grid, LC::THREADS, smem, st>>>(x, bits, frames, window, taps, (int)ntaps, tw, scale, compat);
+}
+
 template <int N>
 static void launch_chain_n(const float2* x, uint8_t* bits, size_t frames, const float2* window, const float2* taps,
                            size_t ntaps, const float2* tw, bool inverse, float scale, int compat, cudaStream_t st) {
-  using LC = ChainLaunch<N>;
-  const size_t smem = (ntaps + (size_t)LC::F * (2 * FftCfg<N>::SMEM_ELEMS + 2 * ntaps)) * sizeof(float2);
-  const size_t want = (frames + LC::F - 1) / LC::F;
-  auto launch = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 1, dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, smem);
-    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);  // grid = SM count x resident CTAs
-    const unsigned grid = (unsigned)(want < resident ? want : resident);
-    kern<<<grid, LC::THREADS, smem, st>>>(x, bits, frames, window, taps, (int)ntaps, tw, scale, compat);
-  };
-  if (inverse) launch(chain_fused_kernel<N, true>);
-  else launch(chain_fused_kernel<N, false>);
+  const bool prune = ntaps - 1 <= (size_t)FftCfg<N>::T;
+  static const char* no_tma = getenv("AE_CHAIN_NO_TMA");
+  const bool staged = ((uintptr_t)x % 16) == 0 && !no_tma;
+#define AE_GO(I, P, S) launch_chain_kernel<N, S>(chain_fused_kernel<N, I, P, S>, x, bits, frames, window, taps, ntaps, tw, scale, compat, st)
+  if (inverse) {
+    if (prune) { if (staged) AE_GO(true, true, true); else AE_GO(true, true, false); }
+    else { if (staged) AE_GO(true, false, true); else AE_GO(true, false, false); }
+  } else {
+    if (prune) { if (staged) AE_GO(false, true, true); else AE_GO(false, true, false); }
+    else { if (staged) AE_GO(false, false, true); else AE_GO(false, false, false); }
+  }
+#undef AE_GO
 }
 
 void launch_chain_fused(const float2* x, uint8_t* bits, size_t nfft, size_t frames, const float2* window, const float2* taps,

@@ -172,7 +172,15 @@ __device__ __forceinline__ void static_for(F&& f) {
 
 // one pass over NB frames that share thread mapping and twiddles.  LAST leaves the result in x
 // (register m <-> position t + m*T), otherwise it is written to the padded shared frames sm[b].
-template <int N, int P, bool INV, int NB>
+//
+// TAIL0: the caller only needs the LAST T bins (register 15) of frame 0.  Everything is fully
+// unrolled register code, so the compiler removes whatever does not feed x[0][15] on its own (the
+// other butterflies of the last pass, their twiddle products, the shared-memory loads); the one thing
+// it cannot see is which STORES of the pass before the last are never read back: with
+// N = 16*NS*Rlast, thread t' = a*NS + k writes output r to position NS*(16a + r) + k, i.e. to
+// register m' = a*(16/Rlast) + floor(r/Rlast) of the last pass, and only m' = q + (16/Rlast) r' with
+// q = 16/Rlast - 1 is consumed  =>  only r >= 16 - Rlast has to be stored.
+template <int N, int P, bool INV, int NB, bool TAIL0 = false>
 __device__ __forceinline__ void fft_pass(float2 (&x)[NB][16], float2* const (&sm)[NB], const float2* __restrict__ tw, int t) {
   using C = FftCfg<N>;
   constexpr int R = C::radix(P);
@@ -219,10 +227,15 @@ __device__ __forceinline__ void fft_pass(float2 (&x)[NB][16], float2* const (&sm
       constexpr int STEP = (NS == 1) ? 1 : (NS + NS / 16);
       if constexpr (NS == 1) a0 = 17 * t;
       else a0 = fft_pad((t - k) * 16 + k);
+      constexpr bool BEFORE_LAST = (P == C::NP - 2);
+      constexpr int RLAST = C::radix(C::NP - 1);
 #pragma unroll
       for (int b = 0; b < NB; ++b)
 #pragma unroll
-        for (int r = 0; r < 16; ++r) sm[b][a0 + r * STEP] = v[b][r];
+        for (int r = 0; r < 16; ++r) {
+          if (TAIL0 && b == 0 && BEFORE_LAST && r < 16 - RLAST) continue;  // never read back
+          sm[b][a0 + r * STEP] = v[b][r];
+        }
     }
   } else {
     // last pass, radix R < 16, B = 16/R butterflies per thread; k = j = t + q*T, TWS == 1
@@ -276,24 +289,32 @@ __device__ __forceinline__ void frame_sync(int f) {
   else asm volatile("bar.sync %0, %1;" ::"r"(f + 1), "r"(T) : "memory");
 }
 
-template <int N, int P, bool INV, int NB>
-__device__ __forceinline__ void fft_passes_from(float2 (&x)[NB][16], float2* const (&sm)[NB], const float2* __restrict__ tw, int t, int f) {
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+// `after_first_sync` runs once, right after the first slot barrier: at that point every thread of
+// the slot has consumed its input registers (used to issue the next frame's TMA copy).
+template <int N, int P, bool INV, int NB, bool TAIL0 = false, class Hook = NoHook>
+__device__ __forceinline__ void fft_passes_from(float2 (&x)[NB][16], float2* const (&sm)[NB], const float2* __restrict__ tw, int t, int f,
+                                                Hook after_first_sync = Hook()) {
   using C = FftCfg<N>;
-  fft_pass<N, P, INV, NB>(x, sm, tw, t);
+  fft_pass<N, P, INV, NB, TAIL0>(x, sm, tw, t);
   if constexpr (P + 1 < C::NP) {
     frame_sync<C::T>(f);
+    if constexpr (P == 0) after_first_sync();
     fft_load_smem<N, NB>(x, sm, t);
     if constexpr (P + 2 < C::NP) frame_sync<C::T>(f);  // WAR: the next pass stores into sm again
-    fft_passes_from<N, P + 1, INV, NB>(x, sm, tw, t, f);
+    fft_passes_from<N, P + 1, INV, NB, TAIL0, NoHook>(x, sm, tw, t, f);
   }
 }
 
 // Full transform of NB frames at once.  x[b]: register m <-> position t + m*T (in and out).
 // The caller must make sure every thread of the frame is past its last shared-memory READ of a
 // previous use of the buffers (frame_sync) before calling this again with the same buffers.
-template <int N, bool INV, int NB>
-__device__ __forceinline__ void fft_frames(float2 (&x)[NB][16], float2* const (&sm)[NB], const float2* __restrict__ tw, int t, int f) {
-  fft_passes_from<N, 0, INV, NB>(x, sm, tw, t, f);
+template <int N, bool INV, int NB, bool TAIL0 = false, class Hook = NoHook>
+__device__ __forceinline__ void fft_frames(float2 (&x)[NB][16], float2* const (&sm)[NB], const float2* __restrict__ tw, int t, int f,
+                                           Hook after_first_sync = Hook()) {
+  fft_passes_from<N, 0, INV, NB, TAIL0, Hook>(x, sm, tw, t, f, after_first_sync);
 }
 
 // single-frame convenience wrapper

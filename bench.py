@@ -297,6 +297,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     ms_per_step = secs_max / args.steps * 1e3
     kernel_s = secs / max(1, launches)  # one kernel per step: launch duration == step duration on this rank
     achieved = ALG_BYTES_PER_SAMPLE * n / kernel_s / 1e9
+    # DRAM traffic of the same kernel from the committed ncu --set full capture, scaled to this launch
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "chain_traffic.json")))
+        traffic = tj["dram_bytes_per_sample"] * n
+    except Exception:
+        pass
 
     # ---- integrity: bits checksum, cross-rank sum (outside the timed region) ----
     ones = torch.count_nonzero(bits).to(torch.int64)
@@ -382,7 +389,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "frames_per_gpu": frames, "samples_per_gpu": n, "compat": "reference", "parallelism": "frames sharded, dp%d" % world,
                        "l2_policy": "inputs larger than L2 (%.1f GiB in, %.1f GiB out per step)" % (8 * n / 2**30, 2 * n / 2**30)},
             "roofline": {"bound": "hbm", "kernel": "chain_fused_kernel<1024>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write per sample from profiles/chain_traffic.json x samples per launch",
+                         "peak_source": peak_src,
                          "alg_bytes_per_sample": ALG_BYTES_PER_SAMPLE, "kernel_ms": kernel_s * 1e3,
                          "fp32_TFLOP/s_nominal": FLOP_PER_SAMPLE * n / kernel_s / 1e12},
             "e2e": e2e, "gpu_launches": launches, "warmup_launches": l_warm, "clocks": clocks,
