@@ -74,6 +74,7 @@ chain_fused_kernel(const float2* __restrict__ x, uint8_t* __restrict__ bits, siz
   }
   __syncthreads();
   const int tm1 = ntaps - 1;
+  const unsigned hi_shift = compat == AE_COMPAT_REFERENCE ? 9u : 8u;  // second byte: idx & 2 vs (idx >> 1) & 1
   uint32_t phase = 0;
   // persistent: every frame slot (C::T threads) walks its own frames and only ever synchronises
   // with itself, so the slots of an SM drift out of phase and overlap their load / compute phases
@@ -132,16 +133,23 @@ chain_fused_kernel(const float2* __restrict__ x, uint8_t* __restrict__ bits, siz
       fix[n] = cx_add(cx_add(a0, a1), cx_add(a2, a3));
     }
 
-    uint8_t* out = bits + 2 * frame * (size_t)N;
+    // hard decisions (src/modulation.rs:33-56).  Fast tie-free test per symbol; the rare symbols that
+    // fail it (near an axis, NaN, inf) are collected in a mask and re-decided exactly afterwards.
+    uint16_t* out = reinterpret_cast<uint16_t*>(bits + 2 * frame * (size_t)N);
+    unsigned risky = 0;
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
       const int n = t + m * C::T;
-      float2 yv = ab[1][m];
-      if (n < tm1) yv = cx_sub(yv, fix[n]);
-      const unsigned idx = demod_qpsk_generic(yv);  // src/modulation.rs:33-56, exact
-      const unsigned b0 = idx & 1u;
-      const unsigned b1 = compat == AE_COMPAT_REFERENCE ? (idx & 2u) : ((idx >> 1) & 1u);
-      *reinterpret_cast<uchar2*>(out + 2 * n) = make_uchar2((unsigned char)b0, (unsigned char)b1);
+      if (m == 0 || !PRUNE) {  // PRUNE: ntaps-1 <= T, only register 0 can hold an output n < ntaps-1
+        if (n < tm1) ab[1][m] = cx_sub(ab[1][m], fix[n]);
+      }
+      if (!qpsk_fast_ok(ab[1][m])) risky |= 1u << m;
+      out[n] = (uint16_t)qpsk_pair_from_signs(ab[1][m], hi_shift);
+    }
+    if (risky) {
+#pragma unroll
+      for (int m = 0; m < 16; ++m)
+        if (risky & (1u << m)) out[t + m * C::T] = (uint16_t)qpsk_pair_from_index(demod_qpsk_exact_slow(ab[1][m]), hi_shift);
     }
   }  // frame loop
 }

@@ -95,6 +95,23 @@ __device__ __forceinline__ unsigned demod_qpsk_generic(float2 s) {
   return demod_qpsk_exact_slow(s);
 }
 
+// Same decision, split for hot loops: qpsk_fast_ok() is the tie-free test, qpsk_sign_index() the
+// sign-based index; callers batch the rare failures and re-decide them with demod_qpsk_exact_slow().
+__device__ __forceinline__ bool qpsk_fast_ok(float2 s) {
+  const float ax = fabsf(s.x), ay = fabsf(s.y);
+  const float u = fmaf(fmaxf(ax, ay), 6.9053396600248786e-4f, 6.9053396600248786e-4f);
+  const float thr = u * u;
+  return ax > thr && ay > thr;
+}
+// the two output bytes of one QPSK symbol as a little-endian u16: byte0 = idx & 1,
+// byte1 = idx & 2 (compat=reference, hi_shift = 9) or (idx >> 1) & 1 (corrected, hi_shift = 8)
+__device__ __forceinline__ unsigned qpsk_pair_from_signs(float2 s, unsigned hi_shift) {
+  return (__float_as_uint(s.x) >> 31) | ((__float_as_uint(s.y) >> 31) << hi_shift);
+}
+__device__ __forceinline__ unsigned qpsk_pair_from_index(unsigned idx, unsigned hi_shift) {
+  return (idx & 1u) | ((idx >> 1) << hi_shift);
+}
+
 // Philox4x32-10 (Salmon et al., Random123).  Known-answer vectors in tests/test_noise.py.
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                        uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
