@@ -6,7 +6,7 @@ NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt
 CSRC      := aether_primitives_b200/csrc
 LIBDIR    := aether_primitives_b200/lib
 OBJDIR    := build/obj
-SRCS      := api elementwise fft fir chain
+SRCS      := api elementwise fft fir chain spectral
 OBJS      := $(addprefix $(OBJDIR)/,$(addsuffix .o,$(SRCS)))
 LIB       := $(LIBDIR)/libaether_b200.so
 ORACLE    := oracle/liboracle.so

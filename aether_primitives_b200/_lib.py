@@ -135,6 +135,13 @@ _SIGS = {
     "ae_chain_exec_host": (None, [_P, _P, _SZ, _P]),
     "ae_chain_exec_unfused": (None, [_P, _P, _P, _P]),
     "ae_ofdm_chain": (None, [_SZ, _SZ, _U64, _F, _U64, _I, _P, _P, _P]),
+    "ae_f32_alloc": (None, [_SZ, C.POINTER(_P)]),
+    "ae_f32_free": (None, [_P]),
+    "ae_f32_len": (_SZ, [_P]),
+    "ae_f32_device_ptr": (None, [_P, C.POINTER(_P)]),
+    "ae_f32_download": (None, [_P, _P, _SZ]),
+    "ae_spectrogram": (None, [_P, _P, _P, _I]),
+    "ae_correlate": (None, [_P, _P, _P, _I, _F, _SZ]),
 }
 
 EXPORTS = tuple(_SIGS.keys())

@@ -1329,4 +1329,118 @@ ae_status ae_ofdm_chain(size_t fft_len, size_t frames, uint64_t first_frame_id, 
   return AE_OK;
 }
 
+// =================================================================================================
+// spectrogram core and correlator
+// =================================================================================================
+}  // extern "C"
+
+struct ae_f32 {
+  Ctx* c;
+  float* p;
+  size_t len, cap;
+};
+
+extern "C" {
+
+ae_status ae_f32_alloc(size_t len, ae_f32** out) {
+  if (!out) return fail(AE_EARG, "null");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  void* p = nullptr;
+  TRY(dev_alloc(c, len * sizeof(float), &p));
+  ae_f32* v = new ae_f32;
+  v->c = c; v->p = (float*)p; v->len = len; v->cap = len;
+  *out = v;
+  return AE_OK;
+}
+ae_status ae_f32_free(ae_f32* v) {
+  if (!v) return AE_OK;
+  cudaSetDevice(v->c->dev);
+  dev_free(v->c, v->p);
+  delete v;
+  return AE_OK;
+}
+size_t ae_f32_len(const ae_f32* v) { return v ? v->len : 0; }
+ae_status ae_f32_device_ptr(ae_f32* v, void** ptr) {
+  if (!v || !ptr) return fail(AE_EARG, "null");
+  *ptr = v->p;
+  return AE_OK;
+}
+ae_status ae_f32_download(ae_f32* v, float* host, size_t n) {
+  if (!v || (!host && n)) return fail(AE_EARG, "null");
+  if (n != v->len) return fail(AE_ELEN, "Vectors must have same length");
+  cudaSetDevice(v->c->dev);
+  if (n) CK(cudaMemcpyAsync(host, v->p, n * sizeof(float), cudaMemcpyDeviceToHost, v->c->stream));
+  return ae_sync();
+}
+
+ae_status ae_spectrogram(ae_fft* f, ae_vec* symbols, ae_f32* levels, int use_db) {
+  if (!f || !symbols || !levels) return fail(AE_EARG, "null");
+  Ctx* c = f->c;
+  cudaSetDevice(c->dev);
+  const size_t n = f->len;
+  const size_t chunks = (symbols->len + n - 1) / n;   // padded.len() % fft_len == 0 (src/util/plot.rs:52-58)
+  const size_t total = chunks * n;
+  if (levels->cap < total) {
+    dev_free(c, levels->p);
+    levels->p = nullptr; levels->cap = 0;
+    void* p;
+    TRY(dev_alloc(c, total * sizeof(float), &p));
+    levels->p = (float*)p; levels->cap = total;
+  }
+  levels->len = total;
+  if (total == 0) return AE_OK;
+  TRY(before_read(symbols));
+  const bool inverse = (f->compat == AE_COMPAT_REFERENCE);  // vec_rfft = Fft::ifwd
+  const float s = scale_factor(AE_SCALE_SN, n, 1.0f);
+  if (f->pow2 && spectral_supported(n)) {
+    launch_spectrogram(vptr(symbols), symbols->len, levels->p, n, chunks, f->tw, inverse, s, use_db, c->stream);
+    CKL(1);
+    return AE_OK;
+  }
+  // any other length: pad, transform with the stand-alone kernels, then mirror + level
+  void* tmp;
+  TRY(dev_alloc(c, total * sizeof(float2), &tmp));
+  CK(cudaMemsetAsync(tmp, 0, total * sizeof(float2), c->stream));
+  CK(cudaMemcpyAsync(tmp, vptr(symbols), symbols->len * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+  ae_status st = fft_run(f, AE_FFT_FWD, (const float2*)tmp, (float2*)tmp, AE_SCALE_SN, 1.0f, chunks);
+  if (st == AE_OK) {
+    launch_levels((const float2*)tmp, levels->p, total, n, use_db, c->stream);
+    g_launches += 1;
+  }
+  dev_free(c, tmp);
+  return st;
+}
+
+ae_status ae_correlate(ae_fft* f, ae_vec* inout, ae_vec* sig, int scale_kind, float x, size_t howmany) {
+  if (!f || !inout || !sig) return fail(AE_EARG, "null");
+  if (scale_kind < 0 || scale_kind > 3) return fail(AE_EARG, "bad scale kind");
+  if (inout->len != f->len * howmany) return fail(AE_ELEN, "Input and FFT must be the same length");  // src/fft.rs:185-189
+  if (sig->len != f->len) return fail(AE_ELEN, "Vectors must have same length");                       // src/vecops.rs:100-104
+  Ctx* c = f->c;
+  cudaSetDevice(c->dev);
+  if (howmany == 0) return AE_OK;
+  TRY(before_write(inout));
+  TRY(before_read(sig));
+  const size_t n = f->len;
+  const float s = scale_factor(scale_kind, n, x);
+  if (f->pow2 && spectral_supported(n)) {
+    launch_correlate(vptr(inout), vptr(sig), n, howmany, f->tw, f->compat == AE_COMPAT_REFERENCE, s, scale_kind != AE_SCALE_NONE,
+                     c->stream);
+    CKL(1);
+    return AE_OK;
+  }
+  // composition of the stand-alone kernels, frame by frame for the multiply
+  TRY(fft_run(f, AE_FFT_FWD, vptr(inout), vptr(inout), scale_kind, x, howmany));
+  for (size_t fr = 0; fr < howmany; ++fr) {
+    TapeParams tp;
+    std::memset(&tp, 0, sizeof(tp));
+    tp.n_ops = 1; tp.load_self = 1;
+    tp.e[0].op = OP_MUL; tp.e[0].operand = vptr(sig);
+    launch_vecops(vptr(inout) + fr * n, n, tp, false, c->sm_count, c->stream);
+    CKL(1);
+  }
+  return fft_run(f, AE_FFT_BWD, vptr(inout), vptr(inout), scale_kind, x, howmany);
+}
+
 }  // extern "C"

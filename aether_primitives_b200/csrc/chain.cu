@@ -14,6 +14,9 @@
 // (A = DFT(x), B = DFT(x .* w)), a triangular fix-up of T(T-1)/2 complex MACs, and the exact
 // reference hard decision on the result:  ~2*50 + 6 + 16 flop/sample instead of 562.
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <vector>
 
 #include "async_copy.cuh"
 #include "fft_device.cuh"
@@ -236,16 +239,17 @@ __device__ __forceinline__ uint32_t lte_mulmod(uint32_t a, uint32_t b) {
 template <int N>
 struct OfdmLaunch {
   static constexpr int T = FftCfg<N>::T;
-  static constexpr int F = T >= 256 ? 1 : (256 / T);
+  static constexpr int F = T >= 128 ? 1 : (128 / T);
   static constexpr int THREADS = F * T;
   static constexpr int WORDS = 2 * N / 32;  // packed bits per frame
   static constexpr size_t SMEM_PER_FRAME = (size_t)FftCfg<N>::SMEM_ELEMS * sizeof(float2) + WORDS * sizeof(uint32_t);
 };
 
 template <int N, bool FWD_INV>  // FWD_INV: exponent sign of Cfft::fwd is + (compat=reference)
-__global__ void __launch_bounds__(OfdmLaunch<N>::THREADS)
+__global__ void __launch_bounds__(OfdmLaunch<N>::THREADS, OfdmLaunch<N>::THREADS <= 128 ? 4 : 2)
 ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int twice, uint64_t seed, const float2* __restrict__ tw,
-                  int compat, uint8_t* __restrict__ tx_bits, uint8_t* __restrict__ rx_bits, ae_stats* stats) {
+                  const uint32_t* __restrict__ zjump, int compat, uint8_t* __restrict__ tx_bits, uint8_t* __restrict__ rx_bits,
+                  ae_stats* stats) {
   using C = FftCfg<N>;
   using LC = OfdmLaunch<N>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -254,121 +258,159 @@ ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int tw
   unsigned char* my = smem_raw + (size_t)f * LC::SMEM_PER_FRAME;
   float2* sm = reinterpret_cast<float2*>(my);
   uint32_t* words = reinterpret_cast<uint32_t*>(my + (size_t)C::SMEM_ELEMS * sizeof(float2));
-  const size_t fl = (size_t)blockIdx.x * LC::F + f;
-  if (fl >= frames) return;
-  const uint64_t frame_id = first_frame + fl;
-
-  // ---- M-sequence words.  WORDS = N/16 = T: exactly one 32-bit word per thread ----
-  {
-    const uint32_t state = (uint32_t)((frame_id + 1) & 0x7fffffffull);  // expand(frame_id+1, 31)
-    // z^(32 t) mod p by square-and-multiply on the (small) exponent
-    uint32_t r = 1u, sq = 2u;
-    unsigned e = 32u * (unsigned)t;
-    while (e) {
-      if (e & 1u) r = lte_mulmod(r, sq);
-      sq = lte_mulmod(sq, sq);
-      e >>= 1;
-    }
-    uint32_t w = 0;
-#pragma unroll 1
-    for (int j = 0; j < 31; ++j) {
-      w |= (uint32_t)(__popc(r & state) & 1) << j;
-      r = lte_mulz(r);
-    }
-    // bit 31 of the word: x[n+31] = x[n+3] ^ x[n]
-    w |= (((w >> 3) ^ w) & 1u) << 31;
-    words[t] = w;
-  }
-  frame_sync<C::T>(f);
-
   const float2 tab[4] = {make_float2(1.0f, 1.0f), make_float2(-1.0f, 1.0f), make_float2(1.0f, -1.0f), make_float2(-1.0f, -1.0f)};
-  float2 v[16];
-  uint32_t txb = 0;  // 2 bits per owned symbol
-#pragma unroll
-  for (int m = 0; m < 16; ++m) {
-    const int pos = t + m * C::T;
-    const uint32_t w = words[pos >> 4];
-    const unsigned two = (w >> ((2 * pos) & 31)) & 3u;  // bit0 = b0, bit1 = b1 -> idx = (b1<<1)+b0
-    txb |= two << (2 * m);
-    v[m] = tab[two];
-  }
-  if (tx_bits) {
-    uint8_t* o = tx_bits + 2 * fl * (size_t)N;
+  const float sn = 1.0f / sqrtf((float)N);  // Scale::SN (src/fft.rs:26)
+  const unsigned hi_shift = compat == AE_COMPAT_REFERENCE ? 9u : 8u;
+  const uint32_t zt = __ldg(zjump + t);  // z^(32 t) mod p(z): frame independent, computed on the host
+  unsigned long long errs = 0;
+  double e_sum = 0.0, r_sum = 0.0;
+  // persistent frame slots (see chain_fused_kernel)
+  for (size_t fl = (size_t)blockIdx.x * LC::F + f; fl < frames; fl += (size_t)gridDim.x * LC::F) {
+    const uint64_t frame_id = first_frame + fl;
+    // ---- M-sequence: WORDS = N/16 = T, exactly one 32-bit word per thread.
+    //      bit j of word t = x[32t + j] = parity( (z^(32t+j) mod p) & state ) ----
+    {
+      const uint32_t state = (uint32_t)((frame_id + 1) & 0x7fffffffull);  // expand(frame_id+1, 31)
+      uint32_t r = zt, w = 0;
+#pragma unroll 4
+      for (int j = 0; j < 31; ++j) {
+        w |= (uint32_t)(__popc(r & state) & 1) << j;
+        r = lte_mulz(r);
+      }
+      w |= (((w >> 3) ^ w) & 1u) << 31;  // x[n+31] = x[n+3] ^ x[n]
+      words[t] = w;
+    }
+    frame_sync<C::T>(f);
+
+    float2 v[16];
+    uint32_t txb = 0;  // 2 bits per owned symbol
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
       const int pos = t + m * C::T;
+      const uint32_t w = words[pos >> 4];
+      const unsigned two = (w >> ((2 * pos) & 31)) & 3u;  // bit0 = b0, bit1 = b1 -> idx = (b1<<1)+b0
+      txb |= two << (2 * m);
+      v[m] = tab[two];
+    }
+    if (tx_bits) {
+      uint16_t* o = reinterpret_cast<uint16_t*>(tx_bits + 2 * fl * (size_t)N);
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const unsigned two = (txb >> (2 * m)) & 3u;
+        o[t + m * C::T] = (uint16_t)((two & 1u) | ((two >> 1) << 8));
+      }
+    }
+    // ---- tx: Cfft::bwd, Scale::SN ----
+    fft_frame<N, !FWD_INV>(v, sm, tw, t, f);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = cx_scale_exact(v[m], sn);
+    // ---- channel ----
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      float2 z0, z1;
+      awgn_unit_pair(seed, frame_id, (uint64_t)(t + m * C::T), z0, z1);
+      z0 = cx_scale_exact(z0, noise_scale); z1 = cx_scale_exact(z1, noise_scale);
+      if (twice) { z0 = cx_scale_exact(z0, noise_scale); z1 = cx_scale_exact(z1, noise_scale); }
+      v[m] = cx_add_exact(v[m], z0);
+      v[m + 8] = cx_add_exact(v[m + 8], z1);
+    }
+    // ---- rx: Cfft::fwd, Scale::SN, demod ----
+    frame_sync<C::T>(f);
+    fft_frame<N, FWD_INV>(v, sm, tw, t, f);
+    float e_pow = 0.0f;
+    unsigned risky = 0, rxb = 0;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      v[m] = cx_scale_exact(v[m], sn);
       const unsigned two = (txb >> (2 * m)) & 3u;
-      *reinterpret_cast<uchar2*>(o + 2 * pos) = make_uchar2((unsigned char)(two & 1u), (unsigned char)(two >> 1));
+      if (!qpsk_fast_ok(v[m])) risky |= 1u << m;
+      rxb |= ((__float_as_uint(v[m].x) >> 31) | ((__float_as_uint(v[m].y) >> 31) << 1)) << (2 * m);
+      const float dr = v[m].x - tab[two].x, di = v[m].y - tab[two].y;
+      e_pow += dr * dr + di * di;
     }
-  }
-  const float sn = 1.0f / sqrtf((float)N);  // Scale::SN (src/fft.rs:26)
-  // ---- tx: Cfft::bwd, Scale::SN ----
-  fft_frame<N, !FWD_INV>(v, sm, tw, t, f);
+    if (risky) {
 #pragma unroll
-  for (int m = 0; m < 16; ++m) v[m] = cx_scale_exact(v[m], sn);
-  // ---- channel ----
-#pragma unroll
-  for (int m = 0; m < 8; ++m) {
-    float2 z0, z1;
-    awgn_unit_pair(seed, frame_id, (uint64_t)(t + m * C::T), z0, z1);
-    z0 = cx_scale_exact(z0, noise_scale); z1 = cx_scale_exact(z1, noise_scale);
-    if (twice) { z0 = cx_scale_exact(z0, noise_scale); z1 = cx_scale_exact(z1, noise_scale); }
-    v[m] = cx_add_exact(v[m], z0);
-    v[m + 8] = cx_add_exact(v[m + 8], z1);
-  }
-  // ---- rx: Cfft::fwd, Scale::SN, demod ----
-  frame_sync<C::T>(f);
-  fft_frame<N, FWD_INV>(v, sm, tw, t, f);
-  unsigned long long errs = 0;
-  float e_pow = 0.0f, r_pow = 0.0f;
-  uint8_t* ro = rx_bits ? rx_bits + 2 * fl * (size_t)N : nullptr;
-#pragma unroll
-  for (int m = 0; m < 16; ++m) {
-    const float2 y = cx_scale_exact(v[m], sn);
-    const unsigned two = (txb >> (2 * m)) & 3u;
-    const unsigned idx = demod_qpsk_generic(y);
-    errs += __popc((idx ^ two) & 3u);
-    const float dr = y.x - tab[two].x, di = y.y - tab[two].y;
-    e_pow += dr * dr + di * di;
-    r_pow += 2.0f;
-    if (ro) {
-      const int pos = t + m * C::T;
-      const unsigned b1 = compat == AE_COMPAT_REFERENCE ? (idx & 2u) : ((idx >> 1) & 1u);
-      *reinterpret_cast<uchar2*>(ro + 2 * pos) = make_uchar2((unsigned char)(idx & 1u), (unsigned char)b1);
+      for (int m = 0; m < 16; ++m)
+        if (risky & (1u << m)) rxb = (rxb & ~(3u << (2 * m))) | (demod_qpsk_exact_slow(v[m]) << (2 * m));
     }
+    errs += __popc(rxb ^ txb);
+    e_sum += (double)e_pow;
+    r_sum += 32.0;  // 16 symbols of power 2
+    if (rx_bits) {
+      uint16_t* ro = reinterpret_cast<uint16_t*>(rx_bits + 2 * fl * (size_t)N);
+#pragma unroll
+      for (int m = 0; m < 16; ++m) ro[t + m * C::T] = (uint16_t)qpsk_pair_from_index((rxb >> (2 * m)) & 3u, hi_shift);
+    }
+    frame_sync<C::T>(f);  // words[] and sm are rewritten by the next frame
   }
   if (stats) {
-    double e = (double)e_pow, r = (double)r_pow;
+    unsigned long long nb = (errs || e_sum > 0.0 || r_sum > 0.0) ? (unsigned long long)(r_sum) : 0ull;  // 32 per frame = 2 bits x 16 symbols
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       errs += __shfl_xor_sync(0xffffffffu, errs, o);
-      e += __shfl_xor_sync(0xffffffffu, e, o);
-      r += __shfl_xor_sync(0xffffffffu, r, o);
+      nb += __shfl_xor_sync(0xffffffffu, nb, o);
+      e_sum += __shfl_xor_sync(0xffffffffu, e_sum, o);
+      r_sum += __shfl_xor_sync(0xffffffffu, r_sum, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0 && nb) {
       atomicAdd(reinterpret_cast<unsigned long long*>(&stats->bit_errors), errs);
-      atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_bits), 32ull * 16ull * 2ull);
-      atomicAdd(&stats->err_pow, e);
-      atomicAdd(&stats->ref_pow, r);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&stats->n_bits), nb);
+      atomicAdd(&stats->err_pow, e_sum);
+      atomicAdd(&stats->ref_pow, r_sum);
     }
   }
 }
 
 bool ofdm_supported(size_t nfft) { return nfft >= 512 && nfft <= 4096 && (nfft & (nfft - 1)) == 0; }
 
+// host: z^(32 t) mod p(z), p = z^31 + z^3 + 1, for t < T
+static uint32_t host_lte_mulz(uint32_t r) {
+  const bool carry = (r >> 30) & 1u;
+  r = (r << 1) & 0x7fffffffu;
+  return carry ? (r ^ (uint32_t)kLteX1PolyLow) : r;
+}
+static const uint32_t* ofdm_jump_table(int T, cudaStream_t st) {
+  static std::map<std::pair<int, int>, uint32_t*> cache;
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  auto key = std::make_pair(dev, T);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  std::vector<uint32_t> h(T);
+  uint32_t r = 1u;
+  for (int t = 0; t < T; ++t) {
+    h[t] = r;
+    for (int j = 0; j < 32; ++j) r = host_lte_mulz(r);
+  }
+  uint32_t* d = nullptr;
+  cudaMalloc((void**)&d, T * sizeof(uint32_t));
+  cudaMemcpyAsync(d, h.data(), T * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+  cache[key] = d;
+  return d;
+}
+
 template <int N>
 static void launch_ofdm_n(size_t frames, uint64_t first_frame, float noise_scale, int twice, uint64_t seed, const float2* tw,
                           int compat, uint8_t* tx_bits, uint8_t* rx_bits, ae_stats* stats, cudaStream_t st) {
   using LC = OfdmLaunch<N>;
   const size_t smem = LC::SMEM_PER_FRAME * LC::F;
-  const unsigned grid = (unsigned)((frames + LC::F - 1) / LC::F);
-  if (compat == AE_COMPAT_REFERENCE) {
-    cudaFuncSetAttribute(ofdm_chain_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ofdm_chain_kernel<N, true><<<grid, LC::THREADS, smem, st>>>(frames, first_frame, noise_scale, twice, seed, tw, compat, tx_bits, rx_bits, stats);
-  } else {
-    cudaFuncSetAttribute(ofdm_chain_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ofdm_chain_kernel<N, false><<<grid, LC::THREADS, smem, st>>>(frames, first_frame, noise_scale, twice, seed, tw, compat, tx_bits, rx_bits, stats);
-  }
+  const size_t want = (frames + LC::F - 1) / LC::F;
+  const uint32_t* zj = ofdm_jump_table(FftCfg<N>::T, st);
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, smem);
+    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+    const unsigned grid = (unsigned)(want < resident ? want : resident);
+    kern<<<grid, LC::THREADS, smem, st>>>(frames, first_frame, noise_scale, twice, seed, tw, zj, compat, tx_bits, rx_bits, stats);
+  };
+  if (compat == AE_COMPAT_REFERENCE) launch(ofdm_chain_kernel<N, true>);
+  else launch(ofdm_chain_kernel<N, false>);
 }
 
 void launch_ofdm_chain(size_t nfft, size_t frames, uint64_t first_frame, float noise_scale, int twice, uint64_t seed,

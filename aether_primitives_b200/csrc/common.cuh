@@ -128,14 +128,22 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// Box-Muller on two 32-bit words -> two independent N(0,1) f32 (full-precision logf/sincospif)
+// Box-Muller on two 32-bit words -> two independent N(0,1) f32.
+// AWGN is validated statistically (tier T2), so the transcendental part uses the SFU:
+//   log : MUFU.LG2-based __logf, except within 2^-6 of 1 where its absolute error would dominate the
+//         tiny result: there log(1 - t) = -t(1 + t/2 + t^2/3 + t^3/4) (t = 1 - u1 is exact);
+//   trig: MUFU-based __sincosf on theta - pi in (-pi, pi], negated (cos/sin(theta) = -cos/sin(theta - pi)).
+// |dz| stays below ~3e-6 sigma of the full-precision evaluation (tests compare with the oracle's).
 __device__ __forceinline__ float2 gauss_pair(uint32_t a, uint32_t b) {
   const float u1 = __fmaf_rn(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
   const float u2 = __fmaf_rn(__uint2float_rn(b), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float r = sqrtf(-2.0f * logf(u1));
+  const float t = 1.0f - u1;
+  const float near1 = -t * fmaf(t, fmaf(t, fmaf(t, 0.25f, 0.33333334f), 0.5f), 1.0f);
+  const float l = t < 0.015625f ? near1 : __logf(u1);
+  const float r = sqrtf(-2.0f * l);
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
-  return make_float2(r * c, r * s);
+  __sincosf(fmaf(u2, 6.28318530717958647692f, -3.14159265358979323846f), &s, &c);
+  return make_float2(-r * c, -r * s);
 }
 
 // unit-variance complex normals for the sample PAIR (2*pair, 2*pair+1) of a stream

@@ -41,8 +41,13 @@ fir_direct_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_t n
   __syncthreads();
   const long long n0 = tile0 + (long long)threadIdx.x * kFirS;
   if ((size_t)n0 >= n) return;
-  // first sample of this thread's frame (frame_len % 8 == 0 guaranteed by the host)
-  const long long fstart = frame_len ? (n0 / (long long)frame_len) * (long long)frame_len : -(1ll << 62);
+  // kz = samples of this thread's frame that precede n0 (frame_len % 8 == 0 guaranteed by the host):
+  // tap k of output n0+s reads x[n0+s-k], which lies before the frame start iff k - s > kz
+  int kz = 0x7fffffff;
+  if (frame_len) {
+    const long long in_frame = n0 % (long long)frame_len;
+    kz = in_frame < (long long)tp ? (int)in_frame : 0x7fffffff;
+  }
   const int base = tp + threadIdx.x * kFirS;  // tile index of x[n0]
   float2 acc[kFirS], w[kFirS];
 #pragma unroll
@@ -59,7 +64,7 @@ fir_direct_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_t n
       // slide: x[n0 - k - 1] replaces the oldest window entry
       const int k1 = kb + kk + 1;
       float2 v = xs[fir_pad(base - k1)];
-      if (n0 - k1 < fstart) v = make_float2(0.0f, 0.0f);
+      if (k1 > kz) v = make_float2(0.0f, 0.0f);  // x[n0 - k1] belongs to the previous frame
       w[(kFirS - 1 - kk) & (kFirS - 1)] = v;
     }
   }

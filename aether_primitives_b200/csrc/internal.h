@@ -82,4 +82,12 @@ void launch_ofdm_chain(size_t nfft, size_t frames, uint64_t first_frame, float n
                        const float2* tw, int compat, uint8_t* tx_bits, uint8_t* rx_bits, ae_stats* stats,
                        cudaStream_t st);
 
+// ---- spectral: spectrogram core and frequency-domain correlator --------------------
+bool spectral_supported(size_t n);
+void launch_spectrogram(const float2* in, size_t n_samples, float* levels, size_t n, size_t frames, const float2* tw, bool inverse,
+                        float scale, int use_db, cudaStream_t st);
+void launch_levels(const float2* spec, float* levels, size_t total, size_t n, int use_db, cudaStream_t st);
+void launch_correlate(float2* data, const float2* sig, size_t n, size_t frames, const float2* tw, bool fwd_inverse, float scale,
+                      int do_scale, cudaStream_t st);
+
 }  // namespace ae

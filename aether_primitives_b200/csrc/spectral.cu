@@ -1,0 +1,169 @@
+// spectral.cu — SURVEY §8(f) "next" rows, built on the K2 device FFT (sm_100a):
+//   spectrogram : the compute core of util::plot::waterfall / spectrum (src/util/plot.rs:46-68,
+//                 :109-130): per fft_len chunk  vec_rfft(Scale::SN) -> vec_mirror -> |.| -> DB::from
+//                 (src/util/mod.rs:26-34), fused into the FFT kernel's epilogue: 8 B in, 4 B out.
+//   correlate   : the frequency-domain correlator the crate benchmarks (benches/benches.rs:410-416):
+//                 vec_rfft(s) -> vec_mul(sig) -> vec_rifft(s) per frame in ONE kernel; the spectrum
+//                 never leaves registers (forward output layout == inverse input layout).
+#include "fft_device.cuh"
+#include "internal.h"
+
+namespace ae {
+
+template <int N>
+struct SpecLaunch {
+  static constexpr int T = FftCfg<N>::T;
+  static constexpr int F = T >= 128 ? 1 : (128 / T);
+  static constexpr int THREADS = F * T;
+  static constexpr size_t SMEM = (size_t)F * FftCfg<N>::SMEM_ELEMS * sizeof(float2);
+};
+
+// level of one (already scaled) bin: c.norm() = hypot (num-complex), then 10*log10 when use_db
+__device__ __forceinline__ float level_of(float2 y, int use_db) {
+  const float nrm = hypotf(y.x, y.y);
+  return use_db ? 10.0f * log10f(nrm) : nrm;
+}
+
+template <int N, bool INV>
+__global__ void __launch_bounds__(SpecLaunch<N>::THREADS, SpecLaunch<N>::THREADS <= 128 ? 4 : 2)
+spectrogram_kernel(const float2* __restrict__ in, size_t n_samples, float* __restrict__ levels, const float2* __restrict__ tw,
+                   size_t frames, float scale, int use_db) {
+  using C = FftCfg<N>;
+  using LC = SpecLaunch<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  const int f = threadIdx.x / C::T;
+  const int t = threadIdx.x % C::T;
+  for (size_t frame = (size_t)blockIdx.x * LC::F + f; frame < frames; frame += (size_t)gridDim.x * LC::F) {
+    const size_t base = frame * N;
+    float2 x[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const size_t g = base + t + m * C::T;
+      x[m] = g < n_samples ? ld_stream(in + g) : make_float2(0.0f, 0.0f);  // zero padding of the last chunk (:52-58)
+    }
+    fft_frame<N, INV>(x, smem + f * C::SMEM_ELEMS, tw, t, f);
+    float* dst = levels + base;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int pos = t + m * C::T;
+      const float2 y = cx_scale_exact(x[m], scale);       // Scale::SN of vec_rfft
+      __stcs(dst + ((pos + N / 2) & (N - 1)), level_of(y, use_db));  // vec_mirror: swap halves
+    }
+    if (C::NP > 1) frame_sync<C::T>(f);
+  }
+}
+
+// fallback epilogue for lengths without a power-of-two kernel: mirror + level of an already
+// transformed and scaled buffer (odd len: the last element of each chunk stays, src/vecops.rs:157-161)
+__global__ void __launch_bounds__(256) levels_kernel(const float2* __restrict__ spec, float* __restrict__ levels, size_t total, size_t n,
+                                                     int use_db) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const size_t fr = i / n, k = i % n, mid = n / 2;
+  size_t src = k;
+  if (k < mid) src = k + mid;
+  else if (k < 2 * mid) src = k - mid;
+  levels[i] = level_of(spec[fr * n + src], use_db);
+}
+
+template <int N>
+static void launch_spec_n(const float2* in, size_t n_samples, float* levels, const float2* tw, size_t frames, bool inverse, float scale,
+                          int use_db, cudaStream_t st) {
+  using LC = SpecLaunch<N>;
+  const size_t want = (frames + LC::F - 1) / LC::F;
+  auto launch = [&](auto kern) {
+    if (LC::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, LC::SMEM);
+    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+    kern<<<(unsigned)(want < resident ? want : resident), LC::THREADS, LC::SMEM, st>>>(in, n_samples, levels, tw, frames, scale, use_db);
+  };
+  if (inverse) launch(spectrogram_kernel<N, true>);
+  else launch(spectrogram_kernel<N, false>);
+}
+
+void launch_spectrogram(const float2* in, size_t n_samples, float* levels, size_t n, size_t frames, const float2* tw, bool inverse,
+                        float scale, int use_db, cudaStream_t st) {
+  if (frames == 0) return;
+  switch (n) {
+#define AE_CASE(NN) case NN: launch_spec_n<NN>(in, n_samples, levels, tw, frames, inverse, scale, use_db, st); break;
+    AE_CASE(16) AE_CASE(32) AE_CASE(64) AE_CASE(128) AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096) AE_CASE(8192)
+#undef AE_CASE
+    default: break;
+  }
+}
+bool spectral_supported(size_t n) { return n >= 16 && n <= 8192 && (n & (n - 1)) == 0; }
+
+void launch_levels(const float2* spec, float* levels, size_t total, size_t n, int use_db, cudaStream_t st) {
+  if (total) levels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(spec, levels, total, n, use_db);
+}
+
+// -------------------------------------------------------------------------------------------------
+// correlator: per frame  x <- bwd( fwd(x)*s1 .* sig )*s2   (benches/benches.rs:410-416)
+// FWD_INV: exponent sign of Cfft::fwd is + (compat=reference); the backward transform uses the other.
+// -------------------------------------------------------------------------------------------------
+template <int N, bool FWD_INV>
+__global__ void __launch_bounds__(SpecLaunch<N>::THREADS, SpecLaunch<N>::THREADS <= 128 ? 4 : 2)
+correlate_kernel(float2* __restrict__ data, const float2* __restrict__ sig, const float2* __restrict__ tw, size_t frames, float scale,
+                 int do_scale) {
+  using C = FftCfg<N>;
+  using LC = SpecLaunch<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* sm = reinterpret_cast<float2*>(smem_raw) + (threadIdx.x / C::T) * C::SMEM_ELEMS;
+  const int f = threadIdx.x / C::T;
+  const int t = threadIdx.x % C::T;
+  for (size_t frame = (size_t)blockIdx.x * LC::F + f; frame < frames; frame += (size_t)gridDim.x * LC::F) {
+    float2* p = data + frame * N;
+    float2 x[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[m] = ld_stream(p + t + m * C::T);
+    fft_frame<N, FWD_INV>(x, sm, tw, t, f);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      if (do_scale) x[m] = cx_scale_exact(x[m], scale);                 // Scale of vec_rfft
+      x[m] = cx_mul_exact(x[m], __ldg(sig + t + m * C::T));             // vec_mul: unfused arithmetic
+    }
+    if (C::NP > 1) frame_sync<C::T>(f);
+    fft_frame<N, !FWD_INV>(x, sm, tw, t, f);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      if (do_scale) x[m] = cx_scale_exact(x[m], scale);                 // Scale of vec_rifft
+      st_stream(p + t + m * C::T, x[m]);
+    }
+    if (C::NP > 1) frame_sync<C::T>(f);
+  }
+}
+
+template <int N>
+static void launch_corr_n(float2* data, const float2* sig, const float2* tw, size_t frames, bool fwd_inverse, float scale, int do_scale,
+                          cudaStream_t st) {
+  using LC = SpecLaunch<N>;
+  const size_t want = (frames + LC::F - 1) / LC::F;
+  auto launch = [&](auto kern) {
+    if (LC::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, LC::SMEM);
+    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+    kern<<<(unsigned)(want < resident ? want : resident), LC::THREADS, LC::SMEM, st>>>(data, sig, tw, frames, scale, do_scale);
+  };
+  if (fwd_inverse) launch(correlate_kernel<N, true>);
+  else launch(correlate_kernel<N, false>);
+}
+
+void launch_correlate(float2* data, const float2* sig, size_t n, size_t frames, const float2* tw, bool fwd_inverse, float scale,
+                      int do_scale, cudaStream_t st) {
+  if (frames == 0) return;
+  switch (n) {
+#define AE_CASE(NN) case NN: launch_corr_n<NN>(data, sig, tw, frames, fwd_inverse, scale, do_scale, st); break;
+    AE_CASE(16) AE_CASE(32) AE_CASE(64) AE_CASE(128) AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096) AE_CASE(8192)
+#undef AE_CASE
+    default: break;
+  }
+}
+
+}  // namespace ae

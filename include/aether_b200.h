@@ -219,6 +219,21 @@ ae_status ae_ofdm_chain(size_t fft_len, size_t frames, uint64_t first_frame_id, 
                         uint64_t noise_seed, int compat, ae_bits* tx_bits /*nullable*/,
                         ae_bits* rx_bits /*nullable*/, ae_stats* device_stats);
 
+/* ---- SURVEY 8(f) "next" rows ----------------------------------------------------------------- */
+typedef struct ae_f32 ae_f32;     /* device Vec<f32> (spectrogram levels) */
+ae_status ae_f32_alloc(size_t len, ae_f32** out);
+ae_status ae_f32_free(ae_f32* v);
+size_t    ae_f32_len(const ae_f32* v);
+ae_status ae_f32_device_ptr(ae_f32* v, void** ptr);
+ae_status ae_f32_download(ae_f32* v, float* host, size_t n);
+/* compute core of util::plot::waterfall / spectrum (src/util/plot.rs:46-68, :109-130): symbols are
+ * zero padded to a multiple of fft.len(); per chunk vec_rfft(Scale::SN) -> vec_mirror -> c.norm() ->
+ * DB::from(..).db() when use_db (src/util/mod.rs:26-34).  levels is resized to chunks*len. */
+ae_status ae_spectrogram(ae_fft* f, ae_vec* symbols, ae_f32* levels, int use_db);
+/* the correlator the crate benchmarks (benches/benches.rs:410-416), in place, `howmany` frames:
+ * input.vec_rfft(&mut fft, s).vec_mul(&sig).vec_rifft(&mut fft, s); sig.len == fft.len() */
+ae_status ae_correlate(ae_fft* f, ae_vec* inout, ae_vec* sig, int scale_kind, float x, size_t howmany);
+
 #ifdef __cplusplus
 }
 #endif

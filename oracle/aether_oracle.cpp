@@ -671,4 +671,41 @@ int ora_ofdm_chain(size_t n, size_t frames, uint64_t first_frame, float noise_po
   return ORA_OK;
 }
 
+// ----------------------------------------------------------------------------------
+// SURVEY 8(f) rows
+// ----------------------------------------------------------------------------------
+// compute core of util::plot::waterfall (src/util/plot.rs:46-68): zero pad to a multiple of
+// fft_len, per chunk vec_rfft(Scale::SN).vec_mirror(), then c.norm() and DB::from (f64 math,
+// src/util/mod.rs:26-34).  levels: chunks*fft_len doubles.
+int ora_spectrogram(const ocf32* sym, size_t n, size_t fft_len, int use_db, int compat, double* levels) {
+  if (fft_len == 0) return ORA_EARG;
+  const size_t chunks = (n + fft_len - 1) / fft_len;
+  std::vector<ocf32> pad(fft_len), out(fft_len);
+  for (size_t c = 0; c < chunks; ++c) {
+    for (size_t i = 0; i < fft_len; ++i) {
+      const size_t g = c * fft_len + i;
+      pad[i] = g < n ? sym[g] : ocf32{0.f, 0.f};
+    }
+    ora_cfft_exec(pad.data(), fft_len, out.data(), fft_len, 1, 0, ORA_SCALE_SN, 1.f, compat);
+    ora_vec_mirror(out.data(), fft_len);
+    for (size_t i = 0; i < fft_len; ++i) {
+      const float nrm = hypotf(out[i].re, out[i].im);
+      levels[c * fft_len + i] = use_db ? 10.0 * std::log10((double)nrm) : (double)nrm;
+    }
+  }
+  return ORA_OK;
+}
+// benches/benches.rs:410-416: input.vec_rfft(&mut fft, s).vec_mul(&sig).vec_rifft(&mut fft, s), per frame
+int ora_correlate(ocf32* data, size_t n, size_t frames, const ocf32* sig, size_t nsig, int scale_kind, float scale_x, int compat) {
+  if (nsig != n) return ORA_ELEN;
+  std::vector<ocf32> tmp(n);
+  for (size_t f = 0; f < frames; ++f) {
+    ocf32* p = data + f * n;
+    ora_cfft_exec(p, n, tmp.data(), n, 1, 0, scale_kind, scale_x, compat);
+    ora_vec_mul(tmp.data(), n, sig, n);
+    ora_cfft_exec(tmp.data(), n, p, n, 1, 1, scale_kind, scale_x, compat);
+  }
+  return ORA_OK;
+}
+
 }  // extern "C"

@@ -60,6 +60,8 @@ def lib():
                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         l.ora_ofdm_chain.argtypes = [C.c_size_t, C.c_size_t, C.c_uint64, C.c_float, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
+        l.ora_spectrogram.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+        l.ora_correlate.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_int]
         _lib = l
     return _lib
 
@@ -257,3 +259,18 @@ def ofdm_chain(n, frames, first_frame, noise_power, seed, compat=REFERENCE):
     _ck(lib().ora_ofdm_chain(n, frames, C.c_uint64(first_frame), float(noise_power), C.c_uint64(seed), compat, _p(tx), _p(rx),
                              _p(stats), _p(sym)))
     return tx, rx, stats, sym
+
+
+# ---- SURVEY 8(f) rows ----------------------------------------------------------------------
+def spectrogram(sym, fft_len, use_db=True, compat=REFERENCE):
+    sym = c64(sym)
+    chunks = (sym.size + fft_len - 1) // fft_len
+    out = np.empty(chunks * fft_len, dtype=np.float64)
+    _ck(lib().ora_spectrogram(_p(sym), sym.size, fft_len, int(use_db), compat, _p(out)))
+    return out
+
+
+def correlate(data, n, sig, scale_kind=SCALE_NONE, scale_x=1.0, compat=REFERENCE):
+    data, sig = c64(data), c64(sig)
+    _ck(lib().ora_correlate(_p(data), n, data.size // n, _p(sig), sig.size, scale_kind, float(scale_x), compat))
+    return data
