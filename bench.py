@@ -232,6 +232,37 @@ def extras(torch, ae, d_in, frames, hbm_peak, steps=5, warmup=3):
         t = timed(torch, lambda: ae.chain.modem_fused(qpsk, g, bits_in, bits_out, st, ae.COMPAT_REFERENCE), steps, warmup) / steps
         rec("modem_fused_%dsym" % nsym, 4.0 * nsym, t, nsym, "symbols")
         del bits_in, bits_out
+    # config 1 stand-alone pieces: modulate, Awgn::apply, Awgn::fill, demod on 2^26 symbols
+    nsym = 1 << 26
+    bits_in = ae.DeviceBits.zeros(2 * nsym)
+    sym = ae.DeviceVec.zeros(nsym)
+    t = timed(torch, lambda: qpsk.modulate_into(bits_in, sym), steps, warmup) / steps
+    rec("modulate_qpsk", 10.0 * nsym, t, nsym, "symbols")
+    t = timed(torch, lambda: g.apply(sym), steps, warmup) / steps
+    rec("awgn_apply", 16.0 * nsym, t, nsym, "samples")
+    fillv = ae.DeviceVec.with_capacity(nsym)
+
+    def fill():
+        fillv.clear()
+        g.fill(fillv)
+    t = timed(torch, fill, steps, warmup) / steps
+    rec("awgn_fill", 8.0 * nsym, t, nsym, "samples")
+    bits_out = ae.DeviceBits.with_capacity(2 * nsym)
+
+    def demod():
+        bits_out.clear()
+        qpsk.demod_naive(sym, bits_out)
+    t = timed(torch, demod, steps, warmup) / steps
+    rec("demod_qpsk", 10.0 * nsym, t, nsym, "symbols")
+    del bits_in, sym, fillv, bits_out
+    # 8(f): spectrogram core (8 B in, 4 B out) and correlator (16 B) on the chain's input
+    lv = ae.spectral.DeviceF32(n)
+    t = timed(torch, lambda: ae.spectral.spectrogram(d_in, fft, True, lv), steps, warmup) / steps
+    rec("spectrogram1024_dB", 12.0 * n, t, n, "samples")
+    del lv
+    sigv = ae.DeviceVec.zeros(FFT_LEN)
+    t = timed(torch, lambda: ae.spectral.correlate(d_in, sigv, fft, ae.Scale.SN, howmany=frames), steps, warmup) / steps
+    rec("correlator1024", 16.0 * n, t, n, "samples")
     # config 5: OFDM-like chain, 2048-pt, 2^16 frames, counters only
     fr = 1 << 16
     t = timed(torch, lambda: ae.chain.ofdm_chain(2048, fr, 0, 0.05, 5, st), steps, warmup) / steps
@@ -409,7 +440,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1 << 20, help="frames per GPU (BASELINE: 2^20)")
