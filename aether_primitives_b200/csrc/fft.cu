@@ -3,8 +3,10 @@
 // folded into the last pass as one separately rounded multiply, which reproduces the
 // reference's "transform, then vec_scale" rounding sequence on this kernel's own output.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
+#include "async_copy.cuh"
 #include "fft_device.cuh"
 #include "internal.h"
 
@@ -20,11 +22,17 @@ struct FftLaunch {
   // frames per CTA: 256-thread CTAs (named barriers allow <= 15 frame slots when T >= 32)
   static constexpr int F = T >= 256 ? 1 : (256 / T);
   static constexpr int THREADS = F * T;
-  static constexpr size_t SMEM = (size_t)F * FftCfg<N>::SMEM_ELEMS * sizeof(float2);
+  static constexpr int MINB = THREADS <= 256 ? 4 : (THREADS <= 512 ? 2 : 1);  // <= 64 registers at 256 threads
+  static constexpr size_t smem(bool staged) {
+    return (size_t)F * (FftCfg<N>::SMEM_ELEMS + (staged ? N : 0)) * sizeof(float2) + (staged ? F * sizeof(uint64_t) : 0);
+  }
 };
 
-template <int N, bool INV>
-__global__ void __launch_bounds__(FftLaunch<N>::THREADS)
+// STAGED: each frame slot prefetches its NEXT frame with one cp.async.bulk (TMA) into a staging buffer
+// while it transforms the current one (mbarrier completion), so twice the bytes are in flight per SM
+// without spending registers; needs a 16-byte aligned input.
+template <int N, bool INV, bool STAGED>
+__global__ void __launch_bounds__(FftLaunch<N>::THREADS, FftLaunch<N>::MINB)
 fft_pow2_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ tw, size_t frames,
                 float scale, int do_scale) {
   using C = FftCfg<N>;
@@ -33,21 +41,57 @@ fft_pow2_kernel(const float2* __restrict__ in, float2* __restrict__ out, const f
   float2* smem = reinterpret_cast<float2*>(smem_raw);
   const int f = threadIdx.x / C::T;
   const int t = threadIdx.x % C::T;
+  float2* sm = smem + (size_t)f * (C::SMEM_ELEMS + (STAGED ? N : 0));
+  float2* xin = sm + C::SMEM_ELEMS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)LC::F * (C::SMEM_ELEMS + (STAGED ? N : 0))) + f;
+  const size_t stride = (size_t)gridDim.x * LC::F;
+  size_t frame = (size_t)blockIdx.x * LC::F + f;
+  if (STAGED) {
+    if (t == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
+      if (frame < frames) {
+        mbar_expect_tx(bar, N * (uint32_t)sizeof(float2));
+        bulk_g2s(xin, in + frame * N, N * (uint32_t)sizeof(float2), bar);
+      }
+    }
+    __syncthreads();
+  }
+  uint32_t phase = 0;
   // persistent: each frame slot (C::T threads) walks its own frames and synchronises only with
   // itself, so the slots resident on an SM drift apart and overlap their load / compute / store phases
-  for (size_t frame = (size_t)blockIdx.x * LC::F + f; frame < frames; frame += (size_t)gridDim.x * LC::F) {
-    const float2* src = in + frame * N;
-    float2 x[16];
+  for (; frame < frames; frame += stride) {
+    float2 x[1][16];
+    if (STAGED) {
+      mbar_wait(bar, phase);
+      phase ^= 1u;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) x[m] = ld_stream(src + t + m * C::T);
-    fft_frame<N, INV>(x, smem + f * C::SMEM_ELEMS, tw, t, f);
+      for (int m = 0; m < 16; ++m) x[0][m] = xin[t + m * C::T];
+    } else {
+      const float2* src = in + frame * N;
+#pragma unroll
+      for (int m = 0; m < 16; ++m) x[0][m] = ld_stream(src + t + m * C::T);
+    }
+    auto prefetch = [&]() {
+      if (STAGED && t == 0 && frame + stride < frames) {
+        mbar_expect_tx(bar, N * (uint32_t)sizeof(float2));
+        bulk_g2s(xin, in + (frame + stride) * N, N * (uint32_t)sizeof(float2), bar);
+      }
+    };
+    float2* const smv[1] = {sm};
+    if (C::NP > 1) {
+      fft_frames<N, INV, 1, false>(x, smv, tw, t, f, prefetch);
+    } else {  // single pass: no slot barrier inside, make one so the staging buffer can be refilled
+      fft_frames<N, INV, 1, false>(x, smv, tw, t, f);
+      if (STAGED) { frame_sync<C::T>(f); prefetch(); }
+    }
     float2* dst = out + frame * N;
     if (do_scale) {
 #pragma unroll
-      for (int m = 0; m < 16; ++m) x[m] = cx_scale_exact(x[m], scale);
+      for (int m = 0; m < 16; ++m) x[0][m] = cx_scale_exact(x[0][m], scale);
     }
 #pragma unroll
-    for (int m = 0; m < 16; ++m) st_stream(dst + t + m * C::T, x[m]);
+    for (int m = 0; m < 16; ++m) st_stream(dst + t + m * C::T, x[0][m]);
     // the next frame's first pass stores into the same shared frame: everyone must be past its reads
     if (C::NP > 1) frame_sync<C::T>(f);
   }
@@ -58,21 +102,24 @@ static void launch_pow2_n(const float2* in, float2* out, size_t frames, const fl
                           float scale, cudaStream_t st) {
   using LC = FftLaunch<N>;
   const size_t want = (frames + LC::F - 1) / LC::F;
-  auto launch = [&](auto kern) {
-    if (LC::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
-    static int resident = 0;  // SM count x resident CTAs per SM, queried once per kernel instantiation
-    if (!resident) {
-      int per_sm = 1, dev = 0, sms = 148;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, LC::SMEM);
-      resident = sms * (per_sm > 0 ? per_sm : 1);
-    }
-    const unsigned grid = (unsigned)(want < (size_t)resident ? want : (size_t)resident);
-    kern<<<grid, LC::THREADS, LC::SMEM, st>>>(in, out, tw, frames, scale, do_scale);
+  // Measured on B200 (tools/fft_quick.py): with 4 CTAs/SM of plain coalesced loads the kernel already
+  // sits at 93-95 % of the measured HBM peak; the TMA-staged variant is 1-3 % slower because its
+  // staging buffers cut the resident CTAs from 4 to 3.  It stays selectable (AE_FFT_TMA=1) and tested.
+  static const char* use_tma = getenv("AE_FFT_TMA");
+  const bool staged = ((uintptr_t)in % 16) == 0 && use_tma && N >= 64 && N <= 2048;
+  auto launch = [&](auto kern, bool stg) {
+    const size_t smem = LC::smem(stg);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, smem);
+    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);  // grid = SM count x resident CTAs
+    const unsigned grid = (unsigned)(want < resident ? want : resident);
+    kern<<<grid, LC::THREADS, smem, st>>>(in, out, tw, frames, scale, do_scale);
   };
-  if (inverse) launch(fft_pow2_kernel<N, true>);
-  else launch(fft_pow2_kernel<N, false>);
+  if (inverse) { if (staged) launch(fft_pow2_kernel<N, true, true>, true); else launch(fft_pow2_kernel<N, true, false>, false); }
+  else { if (staged) launch(fft_pow2_kernel<N, false, true>, true); else launch(fft_pow2_kernel<N, false, false>, false); }
 }
 
 bool fft_pow2_supported(size_t n) { return n >= 16 && n <= 16384 && (n & (n - 1)) == 0; }
