@@ -2,7 +2,7 @@
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr $(EXTRA_NVFLAGS)
 CSRC      := aether_primitives_b200/csrc
 LIBDIR    := aether_primitives_b200/lib
 OBJDIR    := build/obj

@@ -41,8 +41,29 @@ __device__ __forceinline__ float2 cx_mul(float2 a, float2 b) {
 __device__ __forceinline__ float2 cx_mul_conj(float2 a, float2 b) {  // a * conj(b)
   return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
+#ifdef AE_PACKED_F32X2
+// sm_100a packed FP32: one FADD2 adds both halves of a cf32 (same FLOP rate, half the issue slots;
+// measured in tools/ubench/f32x2.cu)
+__device__ __forceinline__ unsigned long long cx_bits(float2 a) {
+  return ((unsigned long long)__float_as_uint(a.y) << 32) | __float_as_uint(a.x);
+}
+__device__ __forceinline__ float2 cx_from_bits(unsigned long long v) {
+  return make_float2(__uint_as_float((unsigned)v), __uint_as_float((unsigned)(v >> 32)));
+}
+__device__ __forceinline__ float2 cx_add(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b)));
+  return cx_from_bits(r);
+}
+__device__ __forceinline__ float2 cx_sub(float2 a, float2 b) {
+  unsigned long long r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(cx_bits(a)), "l"(cx_bits(b)));
+  return cx_from_bits(r);
+}
+#else
 __device__ __forceinline__ float2 cx_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 cx_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 __device__ __forceinline__ void cx_fma(float2& acc, float2 a, float2 b) {  // acc += a*b
   acc.x = fmaf(a.x, b.x, acc.x);
   acc.x = fmaf(-a.y, b.y, acc.x);
