@@ -503,36 +503,35 @@ __device__ __forceinline__ uint64_t gf2_mulmod(uint64_t a, uint64_t b, uint64_t 
   }
   return r;
 }
-constexpr int kMseqBitsPerThread = 256;
+constexpr int kMseqBitsPerThread = 512;
 constexpr int kMseqThreads = 128;
+struct MseqTables {
+  uint64_t pow2[64];              // z^(2^i) mod p
+  uint64_t thread[kMseqThreads];  // z^(kMseqBitsPerThread * t) mod p
+};
+// 4 bits -> 4 bytes of 0/1 (little endian)
+__device__ __forceinline__ uint32_t spread4(uint32_t b) { return ((b & 0xfu) * 0x00204081u) & 0x01010101u; }
+
 // out[i] = x[i], i < len, where x obeys x[n] = parity(window & poly_low) with window bit j = x[n-deg+j]
 // and x[0..deg) = state bits.  Jump-ahead: z^n mod p(z) = sum c_i z^i  =>  x[n] = parity(c & state).
-__global__ void __launch_bounds__(kMseqThreads) mseq_kernel(uint64_t state, uint64_t poly_low, int deg, size_t len, uint8_t* __restrict__ out) {
+// Block start: product of the host-tabulated z^(2^i) over the set bits of the offset (thread 0);
+// thread start: one more multiplication with the tabulated z^(512 t); then 512 bits per thread from a
+// 64-bit sliding window, written as 16-byte vectors.
+__global__ void __launch_bounds__(kMseqThreads) mseq_kernel(uint64_t state, uint64_t poly_low, int deg, size_t len, uint8_t* __restrict__ out,
+                                                            const __grid_constant__ MseqTables tab) {
   __shared__ uint64_t s_block;
   const size_t block_start = (size_t)blockIdx.x * kMseqThreads * kMseqBitsPerThread;
   if (threadIdx.x == 0) {
-    // z^block_start mod p by square-and-multiply
-    uint64_t r = 1ull, sq = (deg == 1) ? poly_low : 2ull;  // z mod p
+    uint64_t r = 1ull;
     size_t e = block_start;
-    while (e) {
-      if (e & 1) r = gf2_mulmod(r, sq, poly_low, deg);
-      sq = gf2_mulmod(sq, sq, poly_low, deg);
-      e >>= 1;
-    }
+    for (int i = 0; e; ++i, e >>= 1)
+      if (e & 1) r = gf2_mulmod(r, tab.pow2[i], poly_low, deg);
     s_block = r;
   }
   __syncthreads();
   const size_t n0 = block_start + (size_t)threadIdx.x * kMseqBitsPerThread;
   if (n0 >= len) return;
-  // z^(256 t) mod p
-  uint64_t r = 1ull, sq = (deg == 1) ? poly_low : 2ull;
-  unsigned e = threadIdx.x * kMseqBitsPerThread;
-  while (e) {
-    if (e & 1) r = gf2_mulmod(r, sq, poly_low, deg);
-    sq = gf2_mulmod(sq, sq, poly_low, deg);
-    e >>= 1;
-  }
-  r = gf2_mulmod(r, s_block, poly_low, deg);
+  uint64_t r = gf2_mulmod(tab.thread[threadIdx.x], s_block, poly_low, deg);
   // first deg bits of this thread's run via successive multiplication by z
   const uint64_t top = 1ull << (deg - 1);
   uint64_t window = 0;
@@ -542,19 +541,52 @@ __global__ void __launch_bounds__(kMseqThreads) mseq_kernel(uint64_t state, uint
     r = (deg == 64) ? (r << 1) : ((r << 1) & ((1ull << deg) - 1ull));
     if (carry) r ^= poly_low;
   }
-  // emit: bits [n0, n0+256); window holds x[n .. n+deg) for the current n
-  size_t n = n0;
+  // emit: window holds x[n .. n+deg) for the current n
   const size_t end = (n0 + kMseqBitsPerThread < len) ? n0 + kMseqBitsPerThread : len;
+  const bool vec_ok = ((uintptr_t)out % 16) == 0;
+  size_t n = n0;
   while (n < end) {
-    const uint8_t bit = (uint8_t)(window & 1ull);
-    out[n++] = bit;
-    const uint64_t nb = (uint64_t)(__popcll(window & poly_low) & 1);
-    window = (window >> 1) | (nb << (deg - 1));
+    uint32_t b16 = 0;
+    const int cnt = (end - n) >= 16 ? 16 : (int)(end - n);
+    for (int i = 0; i < cnt; ++i) {
+      b16 |= (uint32_t)(window & 1ull) << i;
+      const uint64_t nb = (uint64_t)(__popcll(window & poly_low) & 1);
+      window = (window >> 1) | (nb << (deg - 1));
+    }
+    if (cnt == 16 && vec_ok) {
+      *reinterpret_cast<uint4*>(out + n) = make_uint4(spread4(b16), spread4(b16 >> 4), spread4(b16 >> 8), spread4(b16 >> 12));
+    } else {
+      for (int i = 0; i < cnt; ++i) out[n + i] = (uint8_t)((b16 >> i) & 1u);
+    }
+    n += cnt;
   }
+}
+static uint64_t host_gf2_mulmod(uint64_t a, uint64_t b, uint64_t poly_low, int deg) {
+  uint64_t r = 0;
+  const uint64_t top = 1ull << (deg - 1);
+  for (int i = 0; i < deg; ++i) {
+    if ((b >> i) & 1ull) r ^= a;
+    const bool carry = (a & top) != 0;
+    a = (deg == 64) ? (a << 1) : ((a << 1) & ((1ull << deg) - 1ull));
+    if (carry) a ^= poly_low;
+  }
+  return r;
 }
 void launch_mseq(uint64_t state, uint64_t poly_low, int deg, size_t len, uint8_t* out, cudaStream_t st) {
   if (len == 0) return;
-  mseq_kernel<<<cdiv(len, (size_t)kMseqThreads * kMseqBitsPerThread), kMseqThreads, 0, st>>>(state, poly_low, deg, len, out);
+  MseqTables tab;
+  uint64_t sq = (deg == 1) ? poly_low : 2ull;  // z mod p
+  for (int i = 0; i < 64; ++i) {
+    tab.pow2[i] = sq;
+    sq = host_gf2_mulmod(sq, sq, poly_low, deg);
+  }
+  // z^(512 t): 512 = 2^9
+  uint64_t step = tab.pow2[9], r = 1ull;
+  for (int t = 0; t < kMseqThreads; ++t) {
+    tab.thread[t] = r;
+    r = host_gf2_mulmod(r, step, poly_low, deg);
+  }
+  mseq_kernel<<<cdiv(len, (size_t)kMseqThreads * kMseqBitsPerThread), kMseqThreads, 0, st>>>(state, poly_low, deg, len, out, tab);
 }
 
 // =================================================================================================
