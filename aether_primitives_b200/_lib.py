@@ -142,6 +142,9 @@ _SIGS = {
     "ae_f32_download": (None, [_P, _P, _SZ]),
     "ae_spectrogram": (None, [_P, _P, _P, _I]),
     "ae_correlate": (None, [_P, _P, _P, _I, _F, _SZ]),
+    "ae_awgn_next_host": (None, [_P, _P, _SZ]),
+    "ae_vec_read_raw": (None, [C.c_char_p, C.POINTER(_P)]),
+    "ae_vec_write_raw": (None, [_P, C.c_char_p]),
 }
 
 EXPORTS = tuple(_SIGS.keys())

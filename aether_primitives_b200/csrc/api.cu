@@ -1443,4 +1443,71 @@ ae_status ae_correlate(ae_fft* f, ae_vec* inout, ae_vec* sig, int scale_kind, fl
   return fft_run(f, AE_FFT_BWD, vptr(inout), vptr(inout), scale_kind, x, howmany);
 }
 
+ae_status ae_awgn_next_host(ae_awgn* g, ae_cf32* host_out, size_t n) {
+  if (!g || (!host_out && n)) return fail(AE_EARG, "null");
+  if (n == 0) return AE_OK;
+  ae_vec* v;
+  TRY(ae_vec_alloc(0, n, &v));
+  ae_status st = ae_awgn_fill(g, v);                       // NoiseIter::next == Awgn::next (src/noise.rs:81-83)
+  if (st == AE_OK) st = ae_vec_download(v, host_out, n);
+  ae_vec_free(v);
+  return st;
+}
+
+ae_status ae_vec_read_raw(const char* path, ae_vec** out) {
+  if (!path || !out) return fail(AE_EARG, "null");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  FILE* fp = std::fopen(path, "rb");
+  if (!fp) return fail(AE_EARG, std::string("cannot open ") + path);
+  std::fseek(fp, 0, SEEK_END);
+  const long long bytes = std::ftell(fp);
+  std::fseek(fp, 0, SEEK_SET);
+  if (bytes < 0 || bytes % (long long)sizeof(ae_cf32)) {   // count_structs_in_file (src/util/file.rs:12-25)
+    std::fclose(fp);
+    return fail(AE_EARG, "File does not contain an integer number of the requested struct");
+  }
+  const size_t n = (size_t)bytes / sizeof(ae_cf32);
+  ae_vec* v;
+  ae_status st = ae_vec_alloc(n, n, &v);
+  if (st != AE_OK) { std::fclose(fp); return st; }
+  // two pinned staging buffers: read chunk i+1 from disk while chunk i is copied to the device
+  const size_t chunk = (size_t)8 << 20;  // cf32 per chunk (64 MiB)
+  void* stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2];
+  for (int i = 0; i < 2; ++i) {
+    if (cudaHostAlloc(&stage[i], std::min(chunk, std::max<size_t>(n, 1)) * sizeof(ae_cf32), cudaHostAllocDefault) != cudaSuccess) st = fail(AE_EOOM, "pinned staging");
+    cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+  }
+  size_t done = 0;
+  int slot = 0;
+  while (st == AE_OK && done < n) {
+    const size_t k = std::min(chunk, n - done);
+    cudaEventSynchronize(ev[slot]);  // the previous copy out of this buffer has finished
+    if (std::fread(stage[slot], sizeof(ae_cf32), k, fp) != k) { st = fail(AE_EARG, "failed to fill whole buffer"); break; }
+    if (cudaMemcpyAsync(vptr(v) + done, stage[slot], k * sizeof(ae_cf32), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { st = fail(AE_ECUDA, "H2D"); break; }
+    cudaEventRecord(ev[slot], c->stream);
+    done += k;
+    slot ^= 1;
+  }
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 2; ++i) { cudaFreeHost(stage[i]); cudaEventDestroy(ev[i]); }
+  std::fclose(fp);
+  if (st != AE_OK) { ae_vec_free(v); return st; }
+  *out = v;
+  return AE_OK;
+}
+
+ae_status ae_vec_write_raw(ae_vec* v, const char* path) {
+  if (!v || !path) return fail(AE_EARG, "null");
+  std::vector<ae_cf32> h(v->len);
+  TRY(ae_vec_download(v, h.data(), h.size()));
+  FILE* fp = std::fopen(path, "wb");
+  if (!fp) return fail(AE_EARG, std::string("cannot open ") + path);
+  const size_t w = std::fwrite(h.data(), sizeof(ae_cf32), h.size(), fp);
+  std::fclose(fp);
+  if (w != h.size()) return fail(AE_EARG, "short write");
+  return AE_OK;
+}
+
 }  // extern "C"

@@ -45,6 +45,19 @@ class Awgn:
         """:62-66: push noise until len == capacity."""
         call("ae_awgn_fill", self._h, target._h)
 
+    def iter(self, block: int = 4096):
+        """Awgn::iter (:68-70): infinite iterator over the stream (host side, pulled in blocks)."""
+        while True:
+            buf = np.empty(block, dtype=np.complex64)
+            call("ae_awgn_next_host", self._h, buf.ctypes.data_as(C.c_void_p), block)
+            for z in buf:
+                yield z
+
+    def next_host(self, n: int) -> np.ndarray:
+        buf = np.empty(n, dtype=np.complex64)
+        call("ae_awgn_next_host", self._h, buf.ctypes.data_as(C.c_void_p), n)
+        return buf
+
     def __del__(self):
         try:
             if self._h:

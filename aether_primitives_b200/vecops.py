@@ -117,6 +117,17 @@ class DeviceVec:
         assert t.is_cuda and t.is_contiguous() and str(t.dtype) == "torch.complex64"
         return cls.wrap(t.data_ptr(), t.numel(), owner=t)
 
+    @classmethod
+    def from_file(cls, path: str) -> "DeviceVec":
+        """util::file::binary_reader::<cf32> (src/util/file.rs:29-70): raw native-endian cf32, no header."""
+        h = C.c_void_p()
+        call("ae_vec_read_raw", path.encode(), C.byref(h))
+        return cls(h.value)
+
+    def to_file(self, path: str) -> None:
+        """util::file::binary_writer::<cf32> (src/util/file.rs:72-107)."""
+        call("ae_vec_write_raw", self._h, path.encode())
+
     def view(self, start: int, stop: int) -> "DeviceVec":  # &mut v[start..stop]
         if stop < start:
             raise _lib.AeError(_lib.AE_EIDX, "slice index starts at %d but ends at %d" % (start, stop))

@@ -234,6 +234,14 @@ ae_status ae_spectrogram(ae_fft* f, ae_vec* symbols, ae_f32* levels, int use_db)
  * input.vec_rfft(&mut fft, s).vec_mul(&sig).vec_rifft(&mut fft, s); sig.len == fft.len() */
 ae_status ae_correlate(ae_fft* f, ae_vec* inout, ae_vec* sig, int scale_kind, float x, size_t howmany);
 
+/* noise::Awgn::iter() (src/noise.rs:68-84): the next n samples of the stream, to a HOST slice */
+ae_status ae_awgn_next_host(ae_awgn* g, ae_cf32* host_out, size_t n);
+/* sample-file format of util::file (src/util/file.rs:12-107): raw native-endian cf32 structs back to
+ * back, no header.  AE_EARG ("File does not contain an integer number of the requested struct",
+ * :19-22) when the size is not a multiple of 8.  Pinned, chunked staging. */
+ae_status ae_vec_read_raw(const char* path, ae_vec** out);
+ae_status ae_vec_write_raw(ae_vec* v, const char* path);
+
 #ifdef __cplusplus
 }
 #endif

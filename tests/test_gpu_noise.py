@@ -128,3 +128,15 @@ def test_generator_defaults(ae):
     w = ae.DeviceVec.with_capacity(1 << 20)
     g.fill(w)
     assert abs(w.to_numpy().real.var() / 4 - 1) < 0.01
+
+
+def test_iter_and_next_host(ae):
+    g = ae.noise.new(2.0, 9)
+    a = g.next_host(1000)
+    it = g.iter(block=64)
+    b = np.array([next(it) for _ in range(100)], dtype=np.complex64)
+    g2 = ae.noise.new(2.0, 9)
+    v = ae.DeviceVec.with_capacity(1100)
+    g2.fill(v)
+    whole = v.to_numpy()
+    assert np.array_equal(np.concatenate([a, b]).view(np.uint32), whole.view(np.uint32))

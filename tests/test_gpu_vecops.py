@@ -162,3 +162,21 @@ def test_large_fused_chain_property(ae):
     # mirror twice = identity; conj twice = identity
     v.vec_mirror().vec_conj().vec_conj().vec_mirror()
     assert same_bits(v.to_numpy(), want)
+
+
+def test_raw_sample_file_round_trip(ae, tmp_path):
+    """util::file format (src/util/file.rs): raw native-endian cf32 back to back, no header."""
+    x = rnd(3 * (8 << 20) // 2 + 12345, 77, special=False)     # > one 64 MiB staging chunk
+    p = tmp_path / "samples.cf32"
+    x.tofile(p)
+    v = ae.DeviceVec.from_file(str(p))
+    assert len(v) == x.size and same_bits(v.to_numpy(), x)
+    v.vec_conj()
+    q = tmp_path / "out.cf32"
+    v.to_file(str(q))
+    assert same_bits(np.fromfile(q, dtype=np.complex64), o.vec_conj(x))
+    bad = tmp_path / "bad.cf32"
+    bad.write_bytes(b"\\x00" * 13)
+    with pytest.raises(ae.AeError) as e:
+        ae.DeviceVec.from_file(str(bad))
+    assert "integer number of the requested struct" in e.value.message   # src/util/file.rs:19-22
