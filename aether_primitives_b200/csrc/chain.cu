@@ -168,13 +168,20 @@ static void launch_chain_kernel(K kern, const float2* x, uint8_t* bits, size_t f
   const size_t smem = ((size_t)chain_hp((int)ntaps) + (size_t)LC::F * chain_slot_elems<N>((int)ntaps, STAGED)) * sizeof(float2) +
                       (size_t)LC::F * sizeof(uint64_t);
   const size_t want = (frames + LC::F - 1) / LC::F;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int per_sm = 1, dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, smem);
-  const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);  // grid = SM count x resident CTAs
-  const unsigned grid = (unsigned)(want < resident ? want : resident);
+  // grid = SM count x resident CTAs; queried once per (kernel instantiation, shared-memory size)
+  static thread_local size_t cached_smem = 0, cached_resident = 0;
+  static thread_local const void* cached_kern = nullptr;
+  if (cached_smem != smem || cached_kern != (const void*)kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, smem);
+    cached_resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+    cached_smem = smem;
+    cached_kern = (const void*)kern;
+  }
+  const unsigned grid = (unsigned)(want < cached_resident ? want : cached_resident);
   kern<<<grid, LC::THREADS, smem, st>>>(x, bits, frames, window, taps, (int)ntaps, tw, scale, compat);
 }
 

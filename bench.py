@@ -54,56 +54,90 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    """SM clock and throttle reasons sampled every 20 ms DURING the timed region (NVML from a thread;
+    falls back to `nvidia-smi -lms` when pynvml is missing)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+               "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, index: int):
         self.index = index
-        self.lines = []
+        self.samples = []   # (time, sm_mhz, reasons_bitmask)
+        self.max_mhz = None
+        self.stop_flag = False
+        self.thread = None
         self.proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        try:
+                            rs = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            rs = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.samples.append((time.time(), mhz, rs))
+                    except Exception:
+                        pass
+                    time.sleep(0.02)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self._start_smi()
+
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_power_cap,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+            def rd():
+                bits = [0x8, 0x4, 0x40, 0x20]
+                for line in self.proc.stdout:
+                    f = [x.strip() for x in line.split(",")]
+                    try:
+                        self.max_mhz = float(f[1])
+                        rs = sum(b for b, v in zip(bits, f[2:6]) if v.lower().startswith("active"))
+                        self.samples.append((time.time(), float(f[0]), rs))
+                    except Exception:
+                        pass
+
+            self.thread = threading.Thread(target=rd, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
 
     def mark(self):
         return time.time()
 
     def stop(self):
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
 
     def summary(self, t0: float, t1: float) -> dict:
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.25] or [l for (_, l) in self.lines]
-        for l in rows:
-            f = [x.strip() for x in l.split(",")]
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-                for name, val in zip(names, f[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        rows = [(m, r) for (t, m, r) in self.samples if t0 <= t <= t1] or [(m, r) for (_, m, r) in self.samples[-3:]]
+        sm = [m for m, _ in rows]
+        mask = 0
+        for _, r in rows:
+            mask |= r
+        reasons = sorted(n for n, b in self.REASONS.items() if mask & b)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 # ---------------------------------------------------------------------------------------------------
