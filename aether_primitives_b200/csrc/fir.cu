@@ -4,6 +4,8 @@
 // textbook definition  y[n] = sum_{k<T} h[k] x[n-k],  output length = input length, with either
 // a carried history of T-1 samples (streaming) or zero state at the start of every frame.
 // Parity tier T1: EVM against the f64 direct form (tests/test_gpu_fir.py).
+#include <cstdlib>
+
 #include "fft_device.cuh"
 #include "internal.h"
 
@@ -79,9 +81,100 @@ fir_direct_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_t n
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// K3, packed variant.  sm_100a has 2-wide FP32 FMAs (PTX fma.rn.f32x2, SASS FFMA2): the same FLOP
+// rate as FFMA for HALF the issue slots.  A complex MAC  acc += h*x  is two of them,
+//     acc = fma2( (xr, xi), (hr, hr), acc );   acc = fma2( (xi, xr), (-hi, hi), acc );
+// with the tap pairs (hr,hr,-hi,hi) prepared once in shared memory (one 16-byte broadcast read per tap)
+// and the swapped sample (xi, xr) built once per loaded sample and reused by its 8 outputs.  The loop
+// is then bound by the FMA pipe itself instead of by instruction issue.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  return ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+__global__ void __launch_bounds__(kFirThreads)
+fir_direct_x2_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_t n, const float2* __restrict__ taps, int tp,
+                     const float2* __restrict__ history, size_t frame_len) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* hs = reinterpret_cast<float4*>(smem_raw);          // tp entries (hr, hr, -hi, hi)
+  float2* xs = reinterpret_cast<float2*>(hs + tp);            // padded tile: kFirTile + tp inputs
+  const long long tile0 = (long long)blockIdx.x * kFirTile;
+  const int n_in = kFirTile + tp;
+  for (int i = threadIdx.x; i < tp; i += kFirThreads) {
+    const float2 h = __ldg(taps + i);
+    hs[i] = make_float4(h.x, h.x, -h.y, h.y);
+  }
+  for (int i = threadIdx.x; i < n_in; i += kFirThreads) {
+    const long long g = tile0 - tp + i;
+    float2 v = make_float2(0.0f, 0.0f);
+    if (g >= 0) { if ((size_t)g < n) v = ld_stream(x + g); }
+    else if (history && g >= -(long long)(tp - 1)) v = __ldg(history + (tp - 1) + g);
+    xs[fir_pad(i)] = v;
+  }
+  __syncthreads();
+  const long long n0 = tile0 + (long long)threadIdx.x * kFirS;
+  if ((size_t)n0 >= n) return;
+  int kz = 0x7fffffff;
+  if (frame_len) {
+    const long long in_frame = n0 % (long long)frame_len;
+    kz = in_frame < (long long)tp ? (int)in_frame : 0x7fffffff;
+  }
+  const int base = tp + threadIdx.x * kFirS;
+  unsigned long long acc[kFirS], w[kFirS], wsw[kFirS];  // (re, im) accumulators; samples natural and swapped
+#pragma unroll
+  for (int s = 0; s < kFirS; ++s) {
+    acc[s] = 0ull;
+    const float2 v = xs[fir_pad(base + s)];
+    w[s] = f2_pack(v.x, v.y);
+    wsw[s] = f2_pack(v.y, v.x);
+  }
+  for (int kb = 0; kb < tp; kb += kFirS) {
+#pragma unroll
+    for (int kk = 0; kk < kFirS; ++kk) {
+      const float4 h = hs[kb + kk];
+      const unsigned long long ha = f2_pack(h.x, h.y), hb = f2_pack(h.z, h.w);
+#pragma unroll
+      for (int s = 0; s < kFirS; ++s) {
+        const int j = (s - kk) & (kFirS - 1);
+        acc[s] = f2_fma(w[j], ha, acc[s]);
+        acc[s] = f2_fma(wsw[j], hb, acc[s]);
+      }
+      const int k1 = kb + kk + 1;
+      float2 v = xs[fir_pad(base - k1)];
+      if (k1 > kz) v = make_float2(0.0f, 0.0f);
+      const int jn = (kFirS - 1 - kk) & (kFirS - 1);
+      w[jn] = f2_pack(v.x, v.y);
+      wsw[jn] = f2_pack(v.y, v.x);
+    }
+  }
+  if ((size_t)(n0 + kFirS) <= n && ((uintptr_t)(y + n0) % 16) == 0) {
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(y + n0);
+#pragma unroll
+    for (int s = 0; s < kFirS; s += 2) __stcs(o + s / 2, make_ulonglong2(acc[s], acc[s + 1]));
+  } else {
+#pragma unroll
+    for (int s = 0; s < kFirS; ++s)
+      if ((size_t)(n0 + s) < n) y[n0 + s] = make_float2(__uint_as_float((unsigned)acc[s]), __uint_as_float((unsigned)(acc[s] >> 32)));
+  }
+}
+
 void launch_fir_direct(const float2* x, float2* y, size_t n, const float2* taps_padded, int tp, const float2* history,
                        size_t frame_len, int, cudaStream_t st) {
   if (n == 0) return;
+  static const char* scalar = getenv("AE_FIR_SCALAR");
+  if (!scalar) {
+    const size_t n_in2 = (size_t)kFirTile + tp;
+    const size_t smem2 = (size_t)tp * sizeof(float4) + (n_in2 + n_in2 / 8 + 2) * sizeof(float2);
+    if (smem2 > 48 * 1024) cudaFuncSetAttribute(fir_direct_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    fir_direct_x2_kernel<<<(unsigned)((n + kFirTile - 1) / kFirTile), kFirThreads, smem2, st>>>(x, y, n, taps_padded, tp, history, frame_len);
+    return;
+  }
   const size_t n_in = (size_t)kFirTile + tp;
   const size_t smem = ((size_t)tp + n_in + n_in / 8 + 2) * sizeof(float2);
   if (smem > 48 * 1024) cudaFuncSetAttribute(fir_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
