@@ -171,10 +171,13 @@ static void launch_chain_kernel(K kern, const float2* x, uint8_t* bits, size_t f
   // grid = SM count x resident CTAs; queried once per (kernel instantiation, shared-memory size)
   static thread_local size_t cached_smem = 0, cached_resident = 0;
   static thread_local const void* cached_kern = nullptr;
-  if (cached_smem != smem || cached_kern != (const void*)kern) {
+  static thread_local int cached_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cached_smem != smem || cached_kern != (const void*)kern || cached_dev != dev) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 1, dev = 0, sms = 148;
-    cudaGetDevice(&dev);
+    int per_sm = 1, sms = 148;
+    cached_dev = dev;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, smem);
     cached_resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
