@@ -33,9 +33,4 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 print("chain: %.3f ms  %.1f Gsamples/s  %.1f%% of 6534 GB/s" % (ms, frames * n / ms / 1e6, 10 * frames * n / ms / 1e6 / 6534.1 * 100))
-# correctness spot check vs oracle on 4 frames
-from tests import oracle as o
-xs = x[: 4 * n].cpu().numpy()
-wb, ws = o.chain_fft_fir_demod(xs, n, make_taps())
-got = bits[: 8 * n].cpu().numpy()
-print("mismatches vs oracle on 4 frames:", int(np.sum((got != 0) != (wb != 0))))
+# correctness is the job of tests/ (this helper only times the kernel)
