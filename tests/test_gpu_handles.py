@@ -1,0 +1,95 @@
+"""GPU: Vec-like handle semantics behind the C ABI (len/capacity/append/grow/views/wrapped foreign
+memory), i.e. what makes the device types behave like the reference's `Vec<cf32>` / `&mut [cf32]`."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests import oracle as o
+from tests.golden_util import same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(n, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+
+
+def test_append_and_growth_keep_contents(ae):
+    x = rnd(1000, 1)
+    dst = ae.DeviceVec.with_capacity(4)                 # far too small: must grow like Vec::push
+    assert len(dst) == 0 and dst.capacity() == 4
+    ae.sampling.interpolate(ae.DeviceVec.from_numpy(x[:10]), dst, 2)
+    first = dst.to_numpy()
+    ae.sampling.interpolate(ae.DeviceVec.from_numpy(x), dst, 1)     # reallocates; earlier samples survive
+    got = dst.to_numpy()
+    assert len(dst) == first.size + 1999 and dst.capacity() >= len(dst)
+    assert same_bits(got[: first.size], first)
+    assert same_bits(got[first.size:], o.interpolate(x, 1))
+    dst.clear()
+    assert len(dst) == 0 and dst.capacity() >= 2000     # clear keeps the allocation
+
+
+def test_pending_tape_survives_growth_and_set_len(ae):
+    x = rnd(100, 2)
+    v = ae.DeviceVec.with_capacity(100)
+    g = ae.noise.new(1.0, 3)
+    g.fill(v)                                            # len -> capacity
+    base = v.to_numpy()
+    v.vec_scale(2.0)                                     # pending
+    ae.sampling.interpolate(ae.DeviceVec.from_numpy(x), v, 0, ae.COMPAT_CORRECTED)   # append forces a flush + realloc
+    got = v.to_numpy()
+    assert same_bits(got[:100], o.vec_scale(base, 2.0)) and same_bits(got[100:], x)
+
+
+def test_wrapped_foreign_memory(ae):
+    torch = pytest.importorskip("torch")
+    t = torch.view_as_complex(torch.randn(4097, 2, device="cuda"))
+    ref = t.cpu().numpy().copy()
+    v = ae.DeviceVec.from_torch(t)
+    v.vec_conj().vec_scale(3.0).flush()
+    ae.sync()
+    torch.cuda.synchronize()
+    assert same_bits(t.cpu().numpy(), o.vec_scale(o.vec_conj(ref), 3.0))      # the library wrote into torch's buffer
+    with pytest.raises(ae.AeError):
+        ae.sampling.interpolate(ae.DeviceVec.from_numpy(ref), v, 1)           # borrowed memory cannot grow
+    # an 8-byte aligned (not 16) slice of foreign memory takes the scalar paths
+    u = ae.DeviceVec.wrap(t.data_ptr() + 8, 4096, owner=t)
+    u.vec_mirror().flush()
+    ae.sync()
+    want = o.vec_scale(o.vec_conj(ref), 3.0)
+    want[1:] = o.vec_mirror(want[1:])
+    assert same_bits(t.cpu().numpy(), want)
+
+
+def test_bits_handles(ae):
+    b = ae.DeviceBits.with_capacity(2)
+    m = ae.modulation.bpsk()
+    s = rnd(1001, 4)
+    m.demod_naive(ae.DeviceVec.from_numpy(s), b)         # append + grow
+    m.demod_naive(ae.DeviceVec.from_numpy(s[:7]), b)
+    got = b.to_numpy()
+    assert got.size == 1008
+    assert got[:1001].tolist() == o.demod(o.BPSK, s).tolist() and got[1001:].tolist() == o.demod(o.BPSK, s[:7]).tolist()
+    b.clear()
+    assert len(b) == 0
+
+
+def test_pinned_host_alloc_and_stream_switch(ae):
+    lib = ae._lib.lib()
+    p = C.c_void_p()
+    ae._lib.call("ae_host_alloc", 1 << 20, C.byref(p))
+    assert p.value
+    ae._lib.call("ae_host_free", p)
+    torch = pytest.importorskip("torch")
+    x = rnd(5000, 5)
+    v = ae.DeviceVec.from_numpy(x)
+    v.vec_scale(2.0)                                     # recorded on the library stream
+    s = torch.cuda.Stream()
+    ae.set_stream(s.cuda_stream)                         # later work is ordered after earlier work
+    v.vec_conj()
+    got = v.to_numpy()
+    ae.set_stream(None)
+    assert same_bits(got, o.vec_conj(o.vec_scale(x, 2.0)))
+    assert int(lib.ae_launch_count()) > 0
