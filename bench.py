@@ -453,6 +453,33 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     sampler.stop()
     clocks = sampler.summary(t_mark0, t_mark1)
 
+    # ---- BASELINE config 5 on every rank's frame shard: OFDM-like chain, BER/EVM counters summed over
+    #      ranks with the path's only collective (<= 32 bytes per rank, NCCL through torch.distributed)
+    config5 = None
+    try:
+        from aether_primitives_b200.sharding import frame_range
+        from aether_primitives_b200.stats import DeviceStats, allreduce, evm_db
+
+        total_frames = (1 << 16) * world
+        f0, f1 = frame_range(total_frames, rank, world)
+        st = DeviceStats()
+        ofdm = lambda: ae.chain.ofdm_chain(2048, f1 - f0, f0, 0.5, 5, st, None, None, ae.COMPAT_CORRECTED)
+        for _ in range(3):
+            ofdm()
+        st.zero()
+        t5 = timed(torch, ofdm, 5, 0, barrier) / 5
+        local = st.read()
+        tt5 = torch.tensor([t5], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(tt5, op=dist.ReduceOp.MAX)
+        red = allreduce(local)
+        config5 = {"workload": "mseq -> QPSK -> 2048-pt bwd FFT(SN) -> AWGN -> fwd FFT(SN) -> demod -> BER/EVM", "frames_total": total_frames,
+                   "Gsymbols/s": total_frames * 2048 / float(tt5.item()) / 1e9, "ms": float(tt5.item()) * 1e3,
+                   "bit_errors": red["bit_errors"], "n_bits": red["n_bits"], "ber": red["bit_errors"] / max(1, red["n_bits"]),
+                   "evm_db": evm_db(red["err_pow"], red["ref_pow"]), "collective": "all_reduce(sum) of 4 counters, %s" % ("nccl" if dist else "single rank")}
+    except Exception as ex:
+        config5 = {"error": repr(ex)}
+
     extra = None
     cpu = None
     if rank == 0 and world == 1:
@@ -490,6 +517,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             line["cpu_baseline"] = cpu
         if extra:
             line["extra"] = extra
+        if config5:
+            line["config5_ofdm"] = config5
         print(json.dumps(line), flush=True)
     if dist:
         dist.barrier()
