@@ -198,9 +198,78 @@ __global__ void __launch_bounds__(256) fft_generic_pass_kernel(const float2* __r
   out[frame * n + (size_t)(j - k) * p + k + (size_t)q * ns] = acc;
 }
 
+// Any length up to 6144 in ONE kernel: the frame lives in shared memory (two ping-pong buffers), one
+// Stockham pass per factor with the same per-output formula as above; persistent CTAs walk the frames.
+// This is what a batch of N = 100 transforms (the reference's own test length) runs through.
+constexpr int kGenSmemMaxN = 6144;
+constexpr int kGenMaxRadices = 16;
+struct GenRadices { unsigned r[kGenMaxRadices]; int count; };
+
+__global__ void __launch_bounds__(256) fft_generic_smem_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                               const float2* __restrict__ tw, unsigned n, size_t frames,
+                                                               const __grid_constant__ GenRadices rad, int inverse, int do_scale,
+                                                               float scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* buf0 = reinterpret_cast<float2*>(smem_raw);
+  float2* buf1 = buf0 + n;
+  for (size_t frame = blockIdx.x; frame < frames; frame += gridDim.x) {
+    for (unsigned i = threadIdx.x; i < n; i += 256) buf0[i] = ld_stream(in + frame * n + i);
+    __syncthreads();
+    float2* cur = buf0;
+    float2* nxt = buf1;
+    unsigned ns = 1;
+    for (int pi = 0; pi < rad.count; ++pi) {
+      const unsigned p = rad.r[pi], m = n / p, tws = n / (ns * p), wp = n / p;
+      const bool last = (pi == rad.count - 1);
+      for (unsigned o = threadIdx.x; o < n; o += 256) {
+        const unsigned q = o / m, j = o - q * m, k = j % ns;
+        float2 acc = make_float2(0.0f, 0.0f);
+        // exponent of W_n for term r: r*k*tws (< n) + ((r*q) mod p)*wp (< n), both advanced incrementally
+        const unsigned step1 = k * tws;
+        unsigned e1 = 0, rq = 0;
+        for (unsigned r = 0; r < p; ++r) {
+          unsigned e = e1 + rq * wp;
+          if (e >= n) e -= n;
+          float2 w = __ldg(tw + e);
+          if (inverse) w.y = -w.y;
+          cx_fma(acc, cur[j + r * m], w);
+          e1 += step1;
+          rq += q;
+          if (rq >= p) rq -= p;
+        }
+        const unsigned dst = (j - k) * p + k + q * ns;
+        if (last) {
+          if (do_scale) acc = cx_scale_exact(acc, scale);
+          st_stream(out + frame * n + dst, acc);
+        } else {
+          nxt[dst] = acc;
+        }
+      }
+      __syncthreads();
+      float2* t = cur; cur = nxt; nxt = t;
+      ns *= p;
+    }
+  }
+}
+
 void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n, size_t frames, const float2* tw,
                         const uint32_t* radices, int n_radices, bool inverse, bool do_scale, float scale, cudaStream_t st) {
   if (frames == 0 || n == 0) return;
+  if (n <= (size_t)kGenSmemMaxN && n_radices >= 1 && n_radices <= kGenMaxRadices) {
+    GenRadices rad;
+    rad.count = n_radices;
+    for (int i = 0; i < n_radices; ++i) rad.r[i] = radices[i];
+    const size_t smem = 2 * n * sizeof(float2);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fft_generic_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_generic_smem_kernel, 256, smem);
+    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+    fft_generic_smem_kernel<<<(unsigned)(frames < resident ? frames : resident), 256, smem, st>>>(in, out, tw, (unsigned)n, frames, rad, inverse,
+                                                                                                 do_scale, scale);
+    return;
+  }
   // scratch holds 2*n*frames cf32: ping-pong halves; the last pass writes `out`
   constexpr size_t kMaxY = 32768;  // gridDim.y limit is 65535
   for (size_t f0 = 0; f0 < frames; f0 += kMaxY) {
