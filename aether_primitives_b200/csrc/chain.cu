@@ -32,12 +32,12 @@ struct ChainLaunch {
   static constexpr int THREADS = F * T;
   static constexpr int MINB = THREADS <= 128 ? 4 : 2;
 };
-// shared-memory layout (in cf32): [taps, zero padded: HP][per slot: A | B | rt: RP | fix: RP | staging: N if STAGED][mbarriers]
-__host__ __device__ constexpr int chain_hp(int ntaps) { return ((ntaps + 36 + 1) / 2) * 2; }
+// shared-memory layout (in cf32): [taps zero padded: HP][taps shifted by one: HP][per slot: A | B | rt: RP | fixA: RP | fixB: RP | staging: N if STAGED][mbarriers]
+__host__ __device__ constexpr int chain_hp(int ntaps) { return ((ntaps + 68 + 1) / 2) * 2; }
 __host__ __device__ constexpr int chain_rp(int ntaps) { return ((ntaps + 4 + 1) / 2) * 2; }
 template <int N>
 __host__ __device__ constexpr size_t chain_slot_elems(int ntaps, bool staged) {
-  return 2 * (size_t)FftCfg<N>::SMEM_ELEMS + 2 * (size_t)chain_rp(ntaps) + (staged ? N : 0);
+  return 2 * (size_t)FftCfg<N>::SMEM_ELEMS + 3 * (size_t)chain_rp(ntaps) + (staged ? N : 0);
 }
 
 // PRUNE : ntaps-1 <= N/16, so the fix-up only needs register 15 (positions >= N - N/16) of A and
@@ -57,13 +57,18 @@ chain_fused_kernel(const float2* __restrict__ x, uint8_t* __restrict__ bits, siz
   const int t = threadIdx.x % C::T;
   const int HP = chain_hp(ntaps), RP = chain_rp(ntaps);
   const size_t slot = chain_slot_elems<N>(ntaps, STAGED);
-  float2* smA = hs + HP + (size_t)f * slot;
+  float2* hso = hs + HP;              // hso[j] = h[j+1]: makes the pair (h[j+1], h[j+2]) 16-byte aligned for even j
+  float2* smA = hs + 2 * HP + (size_t)f * slot;
   float2* smB = smA + C::SMEM_ELEMS;
   float2* rt = smB + C::SMEM_ELEMS;   // rt[i] = scale * A[N-1-i], zero padded
-  float2* fix = rt + RP;
-  float2* xin = fix + RP;             // STAGED only
-  uint64_t* bar = reinterpret_cast<uint64_t*>(hs + HP + (size_t)LC::F * slot) + f;
-  for (int i = threadIdx.x; i < HP; i += LC::THREADS) hs[i] = i < ntaps ? __ldg(taps + i) : make_float2(0.0f, 0.0f);
+  float2* fix = rt + RP;              // fix-up partial sums A (and the whole sum on the generic path)
+  float2* fixb = fix + RP;            // fix-up partial sums B
+  float2* xin = fixb + RP;            // STAGED only
+  uint64_t* bar = reinterpret_cast<uint64_t*>(hs + 2 * HP + (size_t)LC::F * slot) + f;
+  for (int i = threadIdx.x; i < HP; i += LC::THREADS) {
+    hs[i] = i < ntaps ? __ldg(taps + i) : make_float2(0.0f, 0.0f);
+    hso[i] = i + 1 < ntaps ? __ldg(taps + i + 1) : make_float2(0.0f, 0.0f);
+  }
   for (int i = t; i < RP; i += C::T) rt[i] = make_float2(0.0f, 0.0f);
   const size_t stride = (size_t)gridDim.x * LC::F;
   size_t frame = (size_t)blockIdx.x * LC::F + f;
@@ -117,37 +122,80 @@ chain_fused_kernel(const float2* __restrict__ x, uint8_t* __restrict__ bits, siz
     frame_sync<C::T>(f);
     // wrap-around terms of the circular convolution, outputs n < T-1:
     //   fix[n] = sum_{k=n+1}^{T-1} h[k] A[N+n-k] = sum_{i < T-1-n} h[n+1+i] rt[i]
-    // Taps and rt are zero padded, so every lane of a warp runs the same trip count (the longest
-    // sum of the warp) with no predicates; 4 taps per iteration, rt read as 16-byte broadcasts.
-    // Output n belongs to thread n mod C::T, which is also the thread that consumes it below.
-    for (int n = t; n < tm1; n += C::T) {
-      const int n_first = n - (threadIdx.x & 31);  // first output of this warp
-      const int maxlen = tm1 - (n_first > 0 ? n_first : 0);
-      float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
-      const float2* hp = hs + n + 1;
-      for (int i = 0; i < maxlen; i += 4) {
-        const float4 r01 = *reinterpret_cast<const float4*>(rt + i);
-        const float4 r23 = *reinterpret_cast<const float4*>(rt + i + 2);
-        cx_fma(a0, hp[i], make_float2(r01.x, r01.y));
-        cx_fma(a1, hp[i + 1], make_float2(r01.z, r01.w));
-        cx_fma(a2, hp[i + 2], make_float2(r23.x, r23.y));
-        cx_fma(a3, hp[i + 3], make_float2(r23.z, r23.w));
-      }
-      fix[n] = cx_add(cx_add(a0, a1), cx_add(a2, a3));
-    }
-
-    // hard decisions (src/modulation.rs:33-56).  Fast tie-free test per symbol; the rare symbols that
-    // fail it (near an axis, NaN, inf) are collected in a mask and re-decided exactly afterwards.
+    // Taps and rt are zero padded, so every lane of a warp runs the same trip count with no predicates.
     uint16_t* out = reinterpret_cast<uint16_t*>(bits + 2 * frame * (size_t)N);
     unsigned risky = 0;
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const int n = t + m * C::T;
-      if (m == 0 || !PRUNE) {  // PRUNE: ntaps-1 <= T, only register 0 can hold an output n < ntaps-1
-        if (n < tm1) ab[1][m] = cx_sub(ab[1][m], fix[n]);
+    if (PRUNE) {
+      // (ntaps-1 <= C::T)  The fix-up phase is bound by shared-memory wavefronts, so each thread owns TWO
+      // consecutive outputs (2u, 2u+1): their tap windows overlap, one 16-byte tap read and one 16-byte
+      // broadcast rt read feed four complex MACs (half the wavefronts per MAC of one output per lane).
+      // The first half of the slot's threads sums taps i < H, the second half taps i >= H.
+      const int half = C::T / 2;
+      const int u = t < half ? t : t - half;
+      const int H = ((tm1 / 2) + 1) & ~1;                       // even split point
+      const int lane0_u = u - (int)(threadIdx.x & 31 & (half - 1 < 31 ? half - 1 : 31));
+      const int n_first = 2 * (lane0_u > 0 ? lane0_u : 0);       // first output handled by this warp
+      const int maxlen = tm1 - n_first;                          // longest sum of the warp
+      const int i0 = t < half ? 0 : H;
+      const int i1 = t < half ? (H < maxlen ? H : maxlen) : maxlen;
+      if (2 * u < tm1) {
+        float2 w0a = make_float2(0.0f, 0.0f), w0b = w0a, w1a = w0a, w1b = w0a;
+        const float2* hp = hso + 2 * u;                          // hp[j] = h[2u+1+j]
+        float4 g = *reinterpret_cast<const float4*>(hp + i0);    // (h[n0+1+i], h[n0+2+i])
+        for (int i = i0; i < i1; i += 2) {
+          const float4 gn = *reinterpret_cast<const float4*>(hp + i + 2);
+          const float4 r = *reinterpret_cast<const float4*>(rt + i);
+          const float2 ga = make_float2(g.x, g.y), gb = make_float2(g.z, g.w), gc = make_float2(gn.x, gn.y);
+          const float2 r0 = make_float2(r.x, r.y), r1 = make_float2(r.z, r.w);
+          cx_fma(w0a, ga, r0);
+          cx_fma(w1a, gb, r0);
+          cx_fma(w0b, gb, r1);
+          cx_fma(w1b, gc, r1);
+          g = gn;
+        }
+        float2* dstp = (t < half ? fix : fixb) + 2 * u;
+        *reinterpret_cast<float4*>(dstp) = make_float4(w0a.x + w0b.x, w0a.y + w0b.y, w1a.x + w1b.x, w1a.y + w1b.y);
       }
-      if (!qpsk_fast_ok(ab[1][m])) risky |= 1u << m;
-      out[n] = (uint16_t)qpsk_pair_from_signs(ab[1][m], hi_shift);
+      // meanwhile-independent part: outputs of registers 1..15 never need the fix-up
+#pragma unroll
+      for (int m = 1; m < 16; ++m) {
+        if (!qpsk_fast_ok(ab[1][m])) risky |= 1u << m;
+        out[t + m * C::T] = (uint16_t)qpsk_pair_from_signs(ab[1][m], hi_shift);
+      }
+      frame_sync<C::T>(f);
+      if (t < tm1) {
+        const float2 fa = fix[t], fb = fixb[t];
+        ab[1][0] = cx_sub(ab[1][0], cx_add(fa, fb));
+      }
+      if (!qpsk_fast_ok(ab[1][0])) risky |= 1u;
+      out[t] = (uint16_t)qpsk_pair_from_signs(ab[1][0], hi_shift);
+    } else {
+      // generic path (ntaps-1 > C::T): one output per thread and pass, 4 taps per iteration.
+      // Output n belongs to thread n mod C::T, which is also the thread that consumes it below.
+      for (int n = t; n < tm1; n += C::T) {
+        const int n_first = n - (threadIdx.x & 31);  // first output of this warp
+        const int maxlen = tm1 - (n_first > 0 ? n_first : 0);
+        float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
+        const float2* hp = hs + n + 1;
+        for (int i = 0; i < maxlen; i += 4) {
+          const float4 r01 = *reinterpret_cast<const float4*>(rt + i);
+          const float4 r23 = *reinterpret_cast<const float4*>(rt + i + 2);
+          cx_fma(a0, hp[i], make_float2(r01.x, r01.y));
+          cx_fma(a1, hp[i + 1], make_float2(r01.z, r01.w));
+          cx_fma(a2, hp[i + 2], make_float2(r23.x, r23.y));
+          cx_fma(a3, hp[i + 3], make_float2(r23.z, r23.w));
+        }
+        fix[n] = cx_add(cx_add(a0, a1), cx_add(a2, a3));
+      }
+      // hard decisions (src/modulation.rs:33-56).  Fast tie-free test per symbol; the rare symbols that
+      // fail it (near an axis, NaN, inf) are collected in a mask and re-decided exactly afterwards.
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const int n = t + m * C::T;
+        if (n < tm1) ab[1][m] = cx_sub(ab[1][m], fix[n]);
+        if (!qpsk_fast_ok(ab[1][m])) risky |= 1u << m;
+        out[n] = (uint16_t)qpsk_pair_from_signs(ab[1][m], hi_shift);
+      }
     }
     if (risky) {
 #pragma unroll
@@ -165,7 +213,7 @@ template <int N, bool STAGED, class K>
 static void launch_chain_kernel(K kern, const float2* x, uint8_t* bits, size_t frames, const float2* window, const float2* taps,
                                 size_t ntaps, const float2* tw, float scale, int compat, cudaStream_t st) {
   using LC = ChainLaunch<N>;
-  const size_t smem = ((size_t)chain_hp((int)ntaps) + (size_t)LC::F * chain_slot_elems<N>((int)ntaps, STAGED)) * sizeof(float2) +
+  const size_t smem = (2 * (size_t)chain_hp((int)ntaps) + (size_t)LC::F * chain_slot_elems<N>((int)ntaps, STAGED)) * sizeof(float2) +
                       (size_t)LC::F * sizeof(uint64_t);
   const size_t want = (frames + LC::F - 1) / LC::F;
   // grid = SM count x resident CTAs; queried once per (kernel instantiation, shared-memory size)

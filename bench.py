@@ -507,7 +507,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write per sample from profiles/chain_traffic.json x samples per launch",
                          "peak_source": peak_src,
                          "alg_bytes_per_sample": ALG_BYTES_PER_SAMPLE, "kernel_ms": kernel_s * 1e3,
-                         "limiter": "not HBM: instruction issue 73 % and L1/shared data pipe 80 % busy (ncu, profiles/r1_chain_v7_ncu_summary.txt); "
+                         "limiter": "not HBM: instruction issue 76 % and L1/shared data pipe 77 % busy (ncu, profiles/r1_chain_v8_ncu_summary.txt); "
                                     "two 1024-pt FFTs + fix-up + decisions = ~107 instructions per sample (DESIGN.md 5.2)",
                          "fp32_TFLOP/s_nominal": FLOP_PER_SAMPLE * n / kernel_s / 1e12},
             "e2e": e2e, "gpu_launches": launches, "warmup_launches": l_warm, "clocks": clocks,

@@ -20,7 +20,8 @@ x = torch.view_as_complex(torch.randn(frames * n, 2, device="cuda"))
 bits = torch.empty(2 * frames * n, dtype=torch.uint8, device="cuda")
 d_in = ae.DeviceVec.from_torch(x)
 d_bits = ae.DeviceBits.wrap(bits.data_ptr(), bits.numel(), owner=bits)
-ch = FftFirDemod(n, make_taps(), ae.Scale.SN)
+ntaps = int(os.environ.get('NTAPS', '64'))
+ch = FftFirDemod(n, make_taps(ntaps), ae.Scale.SN)
 for _ in range(3):
     ch.run(d_in, d_bits)
 torch.cuda.synchronize()
@@ -32,5 +33,6 @@ for _ in range(K):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
+print("ntaps=%d" % ntaps, end="  ")
 print("chain: %.3f ms  %.1f Gsamples/s  %.1f%% of 6534 GB/s" % (ms, frames * n / ms / 1e6, 10 * frames * n / ms / 1e6 / 6534.1 * 100))
 # correctness is the job of tests/ (this helper only times the kernel)
