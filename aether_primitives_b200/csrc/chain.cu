@@ -267,8 +267,8 @@ void launch_chain_fused(const float2* x, uint8_t* bits, size_t nfft, size_t fram
 // -------------------------------------------------------------------------------------------------
 // K12 OFDM-like chain (BASELINE config 5).  One frame per frame slot:
 //   bits   : LTE x1 M-sequence x[n] = (x[n-28] + x[n-31]) % 2 (src/sequence.rs:42) seeded with
-//            expand(frame_id + 1, 31) (src/sequence.rs:18-21), 2N bits per frame; each thread jumps to
-//            its own 32-bit word with z^(32 t) mod p(z) and emits it, so no thread waits for another.
+//            expand(frame_id + 1, 31) (src/sequence.rs:18-21), 2N bits per frame; the LFSR is linear, so
+//            each thread XORs the host-tabulated words of the unit-seed sequences selected by the seed bits.
 //   symbols: QPSK table (src/modulation.rs:87-92), idx = (b1<<1)+b0
 //   tx     : Cfft::bwd with Scale::SN            (src/fft.rs:173-182)
 //   channel: Awgn::apply semantics               (src/noise.rs:53-59), Philox stream = frame id,
@@ -277,22 +277,6 @@ void launch_chain_fused(const float2* x, uint8_t* bits, size_t nfft, size_t fram
 // Compulsory HBM traffic: only the audit bits (4 B/symbol) when requested.
 // -------------------------------------------------------------------------------------------------
 constexpr uint64_t kLteX1PolyLow = (1ull << 0) | (1ull << 3);  // p(z) = z^31 + z^3 + 1  (back offsets 31, 28)
-constexpr int kLteDeg = 31;
-
-__device__ __forceinline__ uint32_t lte_mulz(uint32_t r) {  // r * z mod p, deg 31
-  const bool carry = (r >> 30) & 1u;
-  r = (r << 1) & 0x7fffffffu;
-  return carry ? (r ^ (uint32_t)kLteX1PolyLow) : r;
-}
-__device__ __forceinline__ uint32_t lte_mulmod(uint32_t a, uint32_t b) {
-  uint32_t r = 0;
-#pragma unroll 1
-  for (int i = 0; i < kLteDeg; ++i) {
-    if ((b >> i) & 1u) r ^= a;
-    a = lte_mulz(a);
-  }
-  return r;
-}
 
 template <int N>
 struct OfdmLaunch {
@@ -306,7 +290,7 @@ struct OfdmLaunch {
 template <int N, bool FWD_INV>  // FWD_INV: exponent sign of Cfft::fwd is + (compat=reference)
 __global__ void __launch_bounds__(OfdmLaunch<N>::THREADS, OfdmLaunch<N>::THREADS <= 128 ? 4 : 2)
 ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int twice, uint64_t seed, const float2* __restrict__ tw,
-                  const uint32_t* __restrict__ zjump, int compat, uint8_t* __restrict__ tx_bits, uint8_t* __restrict__ rx_bits,
+                  const uint32_t* __restrict__ zcol, int compat, uint8_t* __restrict__ tx_bits, uint8_t* __restrict__ rx_bits,
                   ae_stats* stats) {
   using C = FftCfg<N>;
   using LC = OfdmLaunch<N>;
@@ -319,23 +303,22 @@ ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int tw
   const float2 tab[4] = {make_float2(1.0f, 1.0f), make_float2(-1.0f, 1.0f), make_float2(1.0f, -1.0f), make_float2(-1.0f, -1.0f)};
   const float sn = 1.0f / sqrtf((float)N);  // Scale::SN (src/fft.rs:26)
   const unsigned hi_shift = compat == AE_COMPAT_REFERENCE ? 9u : 8u;
-  const uint32_t zt = __ldg(zjump + t);  // z^(32 t) mod p(z): frame independent, computed on the host
   unsigned long long errs = 0;
   double e_sum = 0.0, r_sum = 0.0;
   // persistent frame slots (see chain_fused_kernel)
   for (size_t fl = (size_t)blockIdx.x * LC::F + f; fl < frames; fl += (size_t)gridDim.x * LC::F) {
     const uint64_t frame_id = first_frame + fl;
-    // ---- M-sequence: WORDS = N/16 = T, exactly one 32-bit word per thread.
-    //      bit j of word t = x[32t + j] = parity( (z^(32t+j) mod p) & state ) ----
+    // ---- M-sequence: WORDS = N/16 = T, exactly one 32-bit word per thread.  The LFSR is linear over
+    //      GF(2): word t of the sequence started from `state` is the XOR, over the set bits i of the
+    //      state, of word t of the sequence started from the unit state e_i (host table zcol[i][t]) ----
     {
-      const uint32_t state = (uint32_t)((frame_id + 1) & 0x7fffffffull);  // expand(frame_id+1, 31)
-      uint32_t r = zt, w = 0;
-#pragma unroll 4
-      for (int j = 0; j < 31; ++j) {
-        w |= (uint32_t)(__popc(r & state) & 1) << j;
-        r = lte_mulz(r);
+      uint32_t state = (uint32_t)((frame_id + 1) & 0x7fffffffull);  // expand(frame_id+1, 31)
+      uint32_t w = 0;
+      while (state) {  // uniform across the slot: one iteration per set seed bit
+        const int i = __ffs(state) - 1;
+        w ^= __ldg(zcol + i * C::T + t);
+        state &= state - 1;
       }
-      w |= (((w >> 3) ^ w) & 1u) << 31;  // x[n+31] = x[n+3] ^ x[n]
       words[t] = w;
     }
     frame_sync<C::T>(f);
@@ -421,13 +404,9 @@ ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int tw
 
 bool ofdm_supported(size_t nfft) { return nfft >= 512 && nfft <= 4096 && (nfft & (nfft - 1)) == 0; }
 
-// host: z^(32 t) mod p(z), p = z^31 + z^3 + 1, for t < T
-static uint32_t host_lte_mulz(uint32_t r) {
-  const bool carry = (r >> 30) & 1u;
-  r = (r << 1) & 0x7fffffffu;
-  return carry ? (r ^ (uint32_t)kLteX1PolyLow) : r;
-}
-static const uint32_t* ofdm_jump_table(int T, cudaStream_t st) {
+// host: zcol[i][t] = bits [32t, 32t+32) of the LTE x1 sequence x[n] = x[n-28] ^ x[n-31] started from the
+// unit state e_i (x[i] = 1, the other 30 seed bits 0), for i < 31 and t < T (= N/16 words = 2N bits)
+static const uint32_t* ofdm_column_table(int T, cudaStream_t st) {
   static std::map<std::pair<int, int>, uint32_t*> cache;
   static std::mutex mu;
   int dev = 0;
@@ -436,15 +415,18 @@ static const uint32_t* ofdm_jump_table(int T, cudaStream_t st) {
   auto key = std::make_pair(dev, T);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
-  std::vector<uint32_t> h(T);
-  uint32_t r = 1u;
-  for (int t = 0; t < T; ++t) {
-    h[t] = r;
-    for (int j = 0; j < 32; ++j) r = host_lte_mulz(r);
+  const size_t nbits = (size_t)T * 32;
+  std::vector<uint32_t> h((size_t)31 * T, 0u);
+  std::vector<uint8_t> x(nbits);
+  for (int i = 0; i < 31; ++i) {
+    for (size_t n = 0; n < 31 && n < nbits; ++n) x[n] = (n == (size_t)i);
+    for (size_t n = 31; n < nbits; ++n) x[n] = x[n - 28] ^ x[n - 31];
+    for (size_t n = 0; n < nbits; ++n)
+      if (x[n]) h[(size_t)i * T + n / 32] |= 1u << (n % 32);
   }
   uint32_t* d = nullptr;
-  cudaMalloc((void**)&d, T * sizeof(uint32_t));
-  cudaMemcpyAsync(d, h.data(), T * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+  cudaMalloc((void**)&d, h.size() * sizeof(uint32_t));
+  cudaMemcpyAsync(d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
   cudaStreamSynchronize(st);
   cache[key] = d;
   return d;
@@ -456,7 +438,7 @@ static void launch_ofdm_n(size_t frames, uint64_t first_frame, float noise_scale
   using LC = OfdmLaunch<N>;
   const size_t smem = LC::SMEM_PER_FRAME * LC::F;
   const size_t want = (frames + LC::F - 1) / LC::F;
-  const uint32_t* zj = ofdm_jump_table(FftCfg<N>::T, st);
+  const uint32_t* zj = ofdm_column_table(FftCfg<N>::T, st);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 1, dev = 0, sms = 148;
