@@ -596,6 +596,9 @@ struct ae_fft {
   int compat;
   float2* tw;
   bool pow2;
+  bool big = false;                       // four-step path (2^15..2^24)
+  float2 *tw1 = nullptr, *tw2 = nullptr;  // per-thread tables of the two factor lengths
+  float2 *wlo = nullptr, *whi = nullptr;  // two-level W_len table (owned)
   std::vector<uint32_t> radices;
   float2* scratch;
   size_t scratch_elems;
@@ -617,6 +620,17 @@ ae_status fft_run(ae_fft* f, int dir, const float2* in, float2* out, int scale_k
   if (f->pow2) {
     launch_fft_pow2(in, out, f->len, howmany, f->tw, inverse, do_scale, s, c->stream);
     CKL(1);
+  } else if (f->big) {
+    const size_t need = f->len * howmany;
+    if (f->scratch_elems < need) {
+      dev_free(c, f->scratch);
+      f->scratch = nullptr; f->scratch_elems = 0;
+      void* p;
+      TRY(dev_alloc(c, need * sizeof(float2), &p));
+      f->scratch = (float2*)p; f->scratch_elems = need;
+    }
+    launch_fft_big(in, out, f->scratch, f->len, howmany, f->tw1, f->tw2, f->wlo, f->whi, inverse, do_scale, s, c->stream);
+    CKL(2 * ((howmany + 32767) / 32768));
   } else {
     const size_t need = 2 * f->len * howmany;
     if (f->scratch_elems < need) {
@@ -647,9 +661,42 @@ ae_status ae_fft_create(size_t len, ae_fft** out) {
   f->c = c; f->len = len; f->compat = AE_COMPAT_REFERENCE;
   f->pow2 = fft_pow2_supported(len);
   f->scratch = nullptr; f->scratch_elems = 0; f->tmp = nullptr; f->tmp_elems = 0;
-  ae_status st = f->pow2 ? get_thread_twiddles(c, len, &f->tw) : get_twiddles(c, len, &f->tw);
+  f->big = !f->pow2 && fft_big_supported(len);
+  ae_status st = AE_OK;
+  if (f->big) {
+    size_t n1, n2;
+    fft_big_split(len, &n1, &n2);
+    st = get_thread_twiddles(c, n1, &f->tw1);
+    if (st == AE_OK) st = get_thread_twiddles(c, n2, &f->tw2);
+    if (st == AE_OK) {
+      std::vector<float2> lo(4096), hi(len / 4096);
+      for (size_t e = 0; e < 4096; ++e) {
+        const double a = -2.0 * M_PI * (double)e / (double)len;
+        lo[e] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+      for (size_t e = 0; e < hi.size(); ++e) {
+        const double a = -2.0 * M_PI * (double)(e * 4096) / (double)len;
+        hi[e] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+      void* p;
+      st = dev_alloc(c, lo.size() * sizeof(float2), &p);
+      if (st == AE_OK) {
+        f->wlo = (float2*)p;
+        cudaMemcpyAsync(f->wlo, lo.data(), lo.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream);
+        st = dev_alloc(c, hi.size() * sizeof(float2), &p);
+      }
+      if (st == AE_OK) {
+        f->whi = (float2*)p;
+        cudaMemcpyAsync(f->whi, hi.data(), hi.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream);
+        cudaStreamSynchronize(c->stream);
+      }
+    }
+    f->tw = nullptr;
+  } else {
+    st = f->pow2 ? get_thread_twiddles(c, len, &f->tw) : get_twiddles(c, len, &f->tw);
+  }
   if (st != AE_OK) { delete f; return st; }
-  if (!f->pow2) {
+  if (!f->pow2 && !f->big) {
     size_t m = len;
     while (m > 1) {
       size_t p = 0;
@@ -671,6 +718,8 @@ ae_status ae_fft_destroy(ae_fft* f) {
   if (!f) return AE_OK;
   cudaSetDevice(f->c->dev);
   dev_free(f->c, f->scratch);
+  dev_free(f->c, f->wlo);
+  dev_free(f->c, f->whi);
   if (f->tmp) { flush_vec(&f->tmpview); alloc_unref(f->c, f->tmp); }
   delete f;
   return AE_OK;

@@ -171,6 +171,117 @@ void launch_fft_pow2(const float2* in, float2* out, size_t n, size_t frames, con
 }
 
 // -------------------------------------------------------------------------------------------------
+// Large power-of-two lengths, 2^15 <= N <= 2^24: four-step FFT, N = N1*N2, as TWO passes of a
+// column-FFT kernel over the frame viewed as a matrix (32 B/sample of traffic instead of one
+// global pass per radix-4 stage):
+//   pass 1: x[n1][n2] -> column FFTs over n1 (length N1, stride N2), times W_N^(n2*k1), written
+//           TRANSPOSED to scratch[n2][k1]
+//   pass 2: scratch[n2][k1] -> column FFTs over n2 (length N2, stride N1), in place by position, so the
+//           result lands at out[k2*N1 + k1] = X[k1 + N1*k2]: natural order, no further transpose.
+// A CTA owns CT adjacent columns; thread = (t, c) with c fastest, so every global access is a run of
+// CT contiguous cf32 per row.  W_N^e is formed from two 4096-entry tables, W^(e>>12 <<12) * W^(e&4095).
+// -------------------------------------------------------------------------------------------------
+template <int N1>
+struct ColLaunch {
+  static constexpr int T = FftCfg<N1>::T;
+  static constexpr int CT = N1 >= 4096 ? 4 : (N1 >= 1024 ? 8 : 16);
+  static constexpr int THREADS = CT * T;
+  // lanes of a warp are different COLUMNS at the same offset: skew each column's buffer by one cf32 so
+  // they fall into different banks (SMEM_ELEMS is a multiple of 16 cf32 = one 128-byte bank row)
+  static constexpr int CSTRIDE = FftCfg<N1>::SMEM_ELEMS + 1;
+  static constexpr size_t SMEM = (size_t)CT * CSTRIDE * sizeof(float2);
+};
+
+template <int N1, bool INV, bool FIRST>
+__global__ void __launch_bounds__(ColLaunch<N1>::THREADS, 1024 / ColLaunch<N1>::THREADS)
+fft_col_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ tw, const float2* __restrict__ wlo,
+               const float2* __restrict__ whi, size_t stride, size_t frame_elems, float scale, int do_scale) {
+  using C = FftCfg<N1>;
+  using LC = ColLaunch<N1>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* smem = reinterpret_cast<float2*>(smem_raw);
+  const int c = threadIdx.x % LC::CT;
+  const int t = threadIdx.x / LC::CT;
+  const size_t col = (size_t)blockIdx.x * LC::CT + c;
+  const float2* src = in + (size_t)blockIdx.y * frame_elems + col;
+  float2 x[1][16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) x[0][m] = ld_stream(src + (size_t)(t + m * C::T) * stride);
+  float2* const smv[1] = {smem + (size_t)c * LC::CSTRIDE};
+  fft_frames<N1, INV, 1, false>(x, smv, tw, t, -1);
+  if (FIRST) {
+    // twiddle W_N^(n2*k1), n2 = col, k1 = t + m*T, then transpose through shared memory
+    __syncthreads();  // every thread is past its last read of the FFT buffers
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const unsigned e = (unsigned)col * (unsigned)(t + m * C::T);  // < N <= 2^24
+      const float2 w = cx_mul(__ldg(whi + (e >> 12)), __ldg(wlo + (e & 4095u)));
+      smv[0][fft_pad(t + m * C::T)] = INV ? cx_mul_conj(x[0][m], w) : cx_mul(x[0][m], w);
+    }
+    __syncthreads();
+    // tile (c, k1) -> scratch[(col0 + c) * N1 + k1]: rows of N1 contiguous cf32
+    float2* dst = out + (size_t)blockIdx.y * frame_elems + (size_t)blockIdx.x * LC::CT * N1;
+    for (int i = threadIdx.x; i < LC::CT * N1; i += LC::THREADS) {
+      const int cc = i / N1, k = i % N1;
+      st_stream(dst + (size_t)cc * N1 + k, smem[(size_t)cc * LC::CSTRIDE + fft_pad(k)]);
+    }
+  } else {
+    float2* dst = out + (size_t)blockIdx.y * frame_elems + col;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      float2 v = x[0][m];
+      if (do_scale) v = cx_scale_exact(v, scale);
+      st_stream(dst + (size_t)(t + m * C::T) * stride, v);
+    }
+  }
+}
+
+template <int N1, bool FIRST>
+static void launch_col_n(const float2* in, float2* out, const float2* tw, const float2* wlo, const float2* whi, size_t ncols,
+                         size_t frames, size_t frame_elems, bool inverse, bool do_scale, float scale, cudaStream_t st) {
+  using LC = ColLaunch<N1>;
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
+    for (size_t f0 = 0; f0 < frames; f0 += 32768) {
+      const size_t fc = frames - f0 < 32768 ? frames - f0 : 32768;
+      const dim3 grid((unsigned)(ncols / LC::CT), (unsigned)fc);
+      kern<<<grid, LC::THREADS, LC::SMEM, st>>>(in + f0 * frame_elems, out + f0 * frame_elems, tw, wlo, whi, ncols, frame_elems, scale,
+                                               do_scale);
+    }
+  };
+  if (inverse) launch(fft_col_kernel<N1, true, FIRST>);
+  else launch(fft_col_kernel<N1, false, FIRST>);
+}
+
+bool fft_big_supported(size_t n) { return n > 16384 && n <= ((size_t)1 << 24) && (n & (n - 1)) == 0; }
+void fft_big_split(size_t n, size_t* n1, size_t* n2) {
+  int l = 0;
+  while (((size_t)1 << l) < n) ++l;
+  *n1 = (size_t)1 << ((l + 1) / 2);
+  *n2 = (size_t)1 << (l / 2);
+}
+
+// in -> scratch (pass 1) -> out (pass 2); scratch holds n*frames cf32; in may equal out
+void launch_fft_big(const float2* in, float2* out, float2* scratch, size_t n, size_t frames, const float2* tw1, const float2* tw2,
+                    const float2* wlo, const float2* whi, bool inverse, bool do_scale, float scale, cudaStream_t st) {
+  if (frames == 0) return;
+  size_t n1, n2;
+  fft_big_split(n, &n1, &n2);
+  switch (n1) {
+#define AE_CASE(NN) case NN: launch_col_n<NN, true>(in, scratch, tw1, wlo, whi, n2, frames, n, inverse, false, 1.0f, st); break;
+    AE_CASE(128) AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096)
+#undef AE_CASE
+    default: return;
+  }
+  switch (n2) {
+#define AE_CASE(NN) case NN: launch_col_n<NN, false>(scratch, out, tw2, wlo, whi, n1, frames, n, inverse, do_scale, scale, st); break;
+    AE_CASE(128) AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096)
+#undef AE_CASE
+    default: return;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // K2b any-length fallback (Cfft::with_len accepts any len; N = 100 is a reference test,
 // src/vecops.rs:445-463).  One global-memory Stockham pass per factor p of N; each thread produces
 // ONE output  out[(j-k)*p + k + q*NS] = sum_r in[j + r*N/p] * W_N^( r*k*N/(NS*p) + ((r*q) mod p)*N/p ).

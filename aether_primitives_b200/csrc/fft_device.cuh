@@ -284,6 +284,7 @@ __device__ __forceinline__ void fft_load_smem(float2 (&x)[NB][16], float2* const
 // barrier among the T threads that own one frame (frame slot f of the CTA)
 template <int T>
 __device__ __forceinline__ void frame_sync(int f) {
+  if (f < 0) { __syncthreads(); return; }  // column kernels: a frame's threads are spread over the CTA
   if (T < 32) __syncwarp();
   else if (T == (int)blockDim.x) __syncthreads();
   else asm volatile("bar.sync %0, %1;" ::"r"(f + 1), "r"(T) : "memory");

@@ -59,6 +59,12 @@ bool fft_pow2_supported(size_t n);
 void fft_thread_twiddles(size_t n, std::vector<float2>& out);
 void launch_fft_pow2(const float2* in, float2* out, size_t n, size_t frames, const float2* tw, bool inverse,
                      bool do_scale, float scale, cudaStream_t st);
+// 2^15..2^24: four-step, two column-FFT passes; tw1/tw2 = per-thread tables of the two factor lengths,
+// wlo[e] = exp(-2 pi i e/n) (e < 4096), whi[e] = exp(-2 pi i 4096 e/n)
+bool fft_big_supported(size_t n);
+void fft_big_split(size_t n, size_t* n1, size_t* n2);
+void launch_fft_big(const float2* in, float2* out, float2* scratch, size_t n, size_t frames, const float2* tw1, const float2* tw2,
+                    const float2* wlo, const float2* whi, bool inverse, bool do_scale, float scale, cudaStream_t st);
 // any length: one global-memory Stockham pass per prime-power factor; needs 2 scratch buffers
 void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n, size_t frames, const float2* tw,
                         const uint32_t* radices, int n_radices, bool inverse, bool do_scale, float scale,

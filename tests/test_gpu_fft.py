@@ -146,3 +146,24 @@ def test_large_batch_properties(ae):
     for fr in rng.integers(0, frames, 8):
         want = o.cfft(x[fr * n:(fr + 1) * n], n, scale_kind=o.SCALE_SN)
         assert evm_db(X[fr * n:(fr + 1) * n], want) <= EVM_LIMIT_DB
+
+
+@pytest.mark.parametrize("n", [1 << 15, 1 << 16, 1 << 17, 1 << 20])
+def test_large_power_of_two_four_step(ae, n):
+    """2^15..2^24: four-step path (two column-FFT passes); same contract as every other length."""
+    frames = 3 if n <= (1 << 17) else 1
+    x = rnd(n * frames, n % 1000)
+    for compat, bwd, sc, ok in ((ae.COMPAT_REFERENCE, False, ae.Scale.SN, o.SCALE_SN), (ae.COMPAT_CORRECTED, True, ae.Scale.None_, o.SCALE_NONE)):
+        f = ae.Cfft.with_len(n, compat)
+        want = o.cfft(x, n, bwd=bwd, scale_kind=ok, compat=compat)
+        din, dout = ae.DeviceVec.from_numpy(x), ae.DeviceVec.zeros(x.size)
+        (f.bwd if bwd else f.fwd)(din, dout, sc, howmany=frames)
+        got = dout.to_numpy()
+        assert evm_db(got, want) <= EVM_LIMIT_DB
+        truth = np.concatenate([(np.fft.ifft(x[i * n:(i + 1) * n].astype(np.complex128)) * n) if ((compat == ae.COMPAT_REFERENCE) != bwd)
+                                else np.fft.fft(x[i * n:(i + 1) * n].astype(np.complex128)) for i in range(frames)])
+        truth = truth * (1.0 / np.sqrt(np.float32(n)) if sc.kind == 1 else 1.0)
+        assert evm_db(got, truth) <= evm_db(want, truth) + 3.02
+        assert same_bits(din.to_numpy(), x)
+        (f.ibwd if bwd else f.ifwd)(din, sc, howmany=frames)      # in place
+        assert same_bits(din.to_numpy(), got)
