@@ -93,3 +93,36 @@ def test_pinned_host_alloc_and_stream_switch(ae):
     ae.set_stream(None)
     assert same_bits(got, o.vec_conj(o.vec_scale(x, 2.0)))
     assert int(lib.ae_launch_count()) > 0
+
+
+def test_empty_inputs_behave_like_empty_slices(ae):
+    """Empty Vec / slice: element-wise ops are no-ops, collectors return empty, and the calls the
+    reference panics on for empty input still fail."""
+    e = ae.DeviceVec.zeros(0)
+    f = ae.DeviceVec.zeros(0)
+    e.vec_scale(2.0).vec_mul(f).vec_conj().vec_mirror().vec_add(f).vec_zero().vec_clone(f).flush()
+    assert len(e) == 0 and e.to_numpy().size == 0
+    m = ae.modulation.qpsk()
+    sym = m.modulate(ae.DeviceBits.zeros(0))                  # chunks() of an empty slice -> empty Vec
+    assert len(sym) == 0
+    out = ae.DeviceBits.with_capacity(1)
+    m.demod_naive(sym, out)
+    assert len(out) == 0
+    fft = ae.Cfft.with_len(64)
+    fft.ifwd(e, ae.Scale.SN, howmany=0)                       # zero frames
+    with pytest.raises(ae.AeError):
+        fft.ifwd(e, ae.Scale.SN)                              # one frame expected: length assert
+    with pytest.raises(ae.AeError):
+        ae.sampling.interpolate(e, ae.DeviceVec.with_capacity(1), 3)      # src.last().unwrap() on empty
+    with pytest.raises(ae.AeError):
+        ae.sampling.downsample(e, ae.DeviceVec.zeros(0))                  # division by zero
+    g = ae.noise.new(1.0, 1)
+    g.apply(e)
+    assert g.tell() == 0
+    from aether_primitives_b200.chain import FftFirDemod
+
+    ch = FftFirDemod(1024, np.ones(4, np.complex64))
+    bits = ae.DeviceBits.with_capacity(1)
+    ch.run(e, bits)                                           # zero frames
+    assert len(bits) == 0
+    assert len(ae.sequence.expand(5, 0)) == 0
