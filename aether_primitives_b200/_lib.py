@@ -32,6 +32,11 @@ class Stats(C.Structure):
     _fields_ = [("bit_errors", C.c_uint64), ("n_bits", C.c_uint64), ("err_pow", C.c_double), ("ref_pow", C.c_double)]
 
 
+class VecStatsRaw(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("min_idx", C.c_uint64), ("max_idx", C.c_uint64), ("min_val", C.c_float), ("max_val", C.c_float),
+                ("sum_re", C.c_double), ("sum_im", C.c_double), ("sum_pow", C.c_double)]
+
+
 _P = C.c_void_p
 _SZ = C.c_size_t
 _I = C.c_int
@@ -140,6 +145,8 @@ _SIGS = {
     "ae_f32_len": (_SZ, [_P]),
     "ae_f32_device_ptr": (None, [_P, C.POINTER(_P)]),
     "ae_f32_download": (None, [_P, _P, _SZ]),
+    "ae_f32_stats": (None, [_P, C.POINTER(VecStatsRaw)]),
+    "ae_vec_stats": (None, [_P, C.POINTER(VecStatsRaw)]),
     "ae_spectrogram": (None, [_P, _P, _P, _I]),
     "ae_correlate": (None, [_P, _P, _P, _I, _F, _SZ]),
     "ae_awgn_next_host": (None, [_P, _P, _SZ]),

@@ -1195,6 +1195,32 @@ ae_status ae_evm_accumulate(ae_vec* act, ae_vec* ref, ae_stats* d) {
   return AE_OK;
 }
 
+static ae_status vecstats_impl(Ctx* c, const void* p, size_t n, bool cplx, ae_vecstats* host_out) {
+  if (!host_out) return fail(AE_EARG, "null");
+  if (n == 0) return fail(AE_ELEN, "VecStats of an empty vector");
+  cudaSetDevice(c->dev);
+  void* scratch = nullptr;
+  const size_t bytes = vecstats_scratch_bytes(c->sm_count);
+  TRY(dev_alloc(c, bytes, &scratch));
+  const int launches = launch_vecstats(p, n, cplx, scratch, c->sm_count, c->stream);
+  ae_status st = AE_OK;
+  if (cudaGetLastError() != cudaSuccess) st = fail(AE_ECUDA, "VecStats launch failed");
+  else {
+    g_launches += launches;
+    const char* res = (const char*)scratch + bytes - sizeof(ae_vecstats);
+    if (cudaMemcpyAsync(host_out, res, sizeof(ae_vecstats), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+      st = fail(AE_ECUDA, "VecStats read-back failed");
+    else st = ae_sync();
+  }
+  dev_free(c, scratch);
+  return st;
+}
+ae_status ae_vec_stats(ae_vec* v, ae_vecstats* host_out) {
+  if (!v) return fail(AE_EARG, "null");
+  TRY(before_read(v));
+  return vecstats_impl(v->c, vptr(v), v->len, true, host_out);
+}
+
 // =================================================================================================
 // fused chains
 // =================================================================================================
@@ -1421,6 +1447,11 @@ ae_status ae_f32_download(ae_f32* v, float* host, size_t n) {
   cudaSetDevice(v->c->dev);
   if (n) CK(cudaMemcpyAsync(host, v->p, n * sizeof(float), cudaMemcpyDeviceToHost, v->c->stream));
   return ae_sync();
+}
+
+ae_status ae_f32_stats(ae_f32* v, ae_vecstats* host_out) {
+  if (!v) return fail(AE_EARG, "null");
+  return vecstats_impl(v->c, v->p, v->len, false, host_out);
 }
 
 ae_status ae_spectrogram(ae_fft* f, ae_vec* symbols, ae_f32* levels, int use_db) {

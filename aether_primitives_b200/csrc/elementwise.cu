@@ -641,4 +641,115 @@ void launch_evm_acc(const float2* act, const float2* ref, size_t n, ae_stats* st
   evm_acc_kernel<<<g, 256, 0, st>>>(act, ref, n, stats);
 }
 
+// =================================================================================================
+// K15 VecStats (README.md:90-92 TODO "VecStats (f32,cf32): Min(index), Max(index), Mean(index), Power";
+// SURVEY 8(f) rank 2).  One read of the vector (8 B/sample cf32, 4 B/sample f32).  cf32 elements are
+// ranked by norm_sqr = re*re + im*im (unfused f32, like num-complex); ties keep the FIRST index, NaN
+// never wins.  Sums are f64.  Two launches: per-CTA partials, then one CTA folds them in a fixed
+// order, so the result does not depend on scheduling.
+// =================================================================================================
+struct StatPart {
+  double sre, sim, spow;
+  float mn, mx;
+  unsigned long long imn, imx;
+};
+constexpr unsigned long long STAT_NONE = ~0ull;
+
+__device__ __forceinline__ void stat_min(float& bv, unsigned long long& bi, float v, unsigned long long i) {
+  if (i == STAT_NONE) return;
+  if (bi == STAT_NONE || v < bv || (v == bv && i < bi)) { bv = v; bi = i; }
+}
+__device__ __forceinline__ void stat_max(float& bv, unsigned long long& bi, float v, unsigned long long i) {
+  if (i == STAT_NONE) return;
+  if (bi == STAT_NONE || v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+}
+__device__ __forceinline__ void stat_merge(StatPart& a, const StatPart& b) {
+  a.sre += b.sre; a.sim += b.sim; a.spow += b.spow;
+  stat_min(a.mn, a.imn, b.mn, b.imn);
+  stat_max(a.mx, a.imx, b.mx, b.imx);
+}
+__device__ __forceinline__ StatPart stat_shfl(const StatPart& p, int o) {
+  StatPart q;
+  q.sre = __shfl_xor_sync(0xffffffffu, p.sre, o);
+  q.sim = __shfl_xor_sync(0xffffffffu, p.sim, o);
+  q.spow = __shfl_xor_sync(0xffffffffu, p.spow, o);
+  q.mn = __shfl_xor_sync(0xffffffffu, p.mn, o);
+  q.mx = __shfl_xor_sync(0xffffffffu, p.mx, o);
+  q.imn = __shfl_xor_sync(0xffffffffu, p.imn, o);
+  q.imx = __shfl_xor_sync(0xffffffffu, p.imx, o);
+  return q;
+}
+// fold the CTA's 256 partials; thread 0 returns the result
+__device__ __forceinline__ StatPart stat_block_fold(StatPart p) {
+  __shared__ StatPart sh[8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { const StatPart q = stat_shfl(p, o); stat_merge(p, q); }
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = p;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    p = sh[0];
+    for (int w = 1; w < 8; ++w) stat_merge(p, sh[w]);
+  }
+  return p;
+}
+
+template <bool CPLX>
+__device__ __forceinline__ void stat_take(StatPart& p, const void* base, size_t i) {
+  float v;
+  if (CPLX) {
+    const float2 x = __ldcs((const float2*)base + i);
+    v = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
+    p.sre += (double)x.x; p.sim += (double)x.y; p.spow += (double)x.x * (double)x.x + (double)x.y * (double)x.y;
+  } else {
+    v = __ldcs((const float*)base + i);
+    p.sre += (double)v; p.spow += (double)v * (double)v;
+  }
+  if (v == v) {                                   // NaN is never a minimum or a maximum
+    if (p.imn == STAT_NONE || v < p.mn) { p.mn = v; p.imn = i; }
+    if (p.imx == STAT_NONE || v > p.mx) { p.mx = v; p.imx = i; }
+  }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256) vecstats_kernel(const void* __restrict__ v, size_t n, StatPart* __restrict__ parts) {
+  StatPart p{0.0, 0.0, 0.0, 0.f, 0.f, STAT_NONE, STAT_NONE};
+  const size_t stride = (size_t)gridDim.x * 256;
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {   // four independent loads in flight
+    stat_take<CPLX>(p, v, i);
+    stat_take<CPLX>(p, v, i + stride);
+    stat_take<CPLX>(p, v, i + 2 * stride);
+    stat_take<CPLX>(p, v, i + 3 * stride);
+  }
+  for (; i < n; i += stride) stat_take<CPLX>(p, v, i);
+  p = stat_block_fold(p);
+  if (threadIdx.x == 0) parts[blockIdx.x] = p;
+}
+__global__ void __launch_bounds__(256) vecstats_fold_kernel(const StatPart* __restrict__ parts, unsigned nparts, size_t n, ae_vecstats* out) {
+  StatPart p{0.0, 0.0, 0.0, 0.f, 0.f, STAT_NONE, STAT_NONE};
+  for (unsigned k = threadIdx.x; k < nparts; k += 256) stat_merge(p, parts[k]);
+  p = stat_block_fold(p);
+  if (threadIdx.x == 0) {
+    out->n = n;
+    out->min_idx = p.imn == STAT_NONE ? n : p.imn;
+    out->max_idx = p.imx == STAT_NONE ? n : p.imx;
+    out->min_val = p.mn; out->max_val = p.mx;
+    out->sum_re = p.sre; out->sum_im = p.sim; out->sum_pow = p.spow;
+  }
+}
+
+size_t vecstats_scratch_bytes(int sm_count) { return (size_t)sm_count * 8 * sizeof(StatPart) + sizeof(ae_vecstats); }
+int launch_vecstats(const void* v, size_t n, bool cplx, void* scratch, int sm_count, cudaStream_t st) {
+  unsigned g = cdiv(n, 256 * 8);
+  const unsigned cap = (unsigned)sm_count * 8;
+  if (g > cap) g = cap;
+  if (g == 0) g = 1;
+  StatPart* parts = (StatPart*)scratch;
+  ae_vecstats* out = (ae_vecstats*)((char*)scratch + (size_t)sm_count * 8 * sizeof(StatPart));
+  if (cplx) vecstats_kernel<true><<<g, 256, 0, st>>>(v, n, parts);
+  else vecstats_kernel<false><<<g, 256, 0, st>>>(v, n, parts);
+  vecstats_fold_kernel<<<1, 256, 0, st>>>(parts, g, n, out);
+  return 2;
+}
+
 }  // namespace ae

@@ -51,6 +51,9 @@ void launch_mseq(uint64_t state, uint64_t poly_low, int deg, size_t len, uint8_t
 // ---- K13 statistics --------------------------------------------------------------------------
 void launch_bit_errors(const uint8_t* a, const uint8_t* b, size_t n, ae_stats* stats, int sm_count, cudaStream_t st);
 void launch_evm_acc(const float2* act, const float2* ref, size_t n, ae_stats* stats, int sm_count, cudaStream_t st);
+// VecStats: scratch = per-CTA partials followed by the ae_vecstats result; returns the launch count
+size_t vecstats_scratch_bytes(int sm_count);
+int launch_vecstats(const void* v, size_t n, bool cplx, void* scratch, int sm_count, cudaStream_t st);
 
 // ---- K2 FFT ----------------------------------------------------------------------------------
 // power-of-two register/shared-memory kernel, 16 <= n <= 16384.  `tw` of every power-of-two launcher

@@ -39,6 +39,15 @@ class DeviceF32:
         call("ae_f32_download", self._h, out.ctypes.data_as(C.c_void_p), out.size)
         return out
 
+    def vec_stats(self):
+        """VecStats of the f32 vector (min/max by value); see `stats.VecStats`."""
+        from . import _lib
+        from .stats import VecStats
+
+        raw = _lib.VecStatsRaw()
+        call("ae_f32_stats", self._h, C.byref(raw))
+        return VecStats(raw, False)
+
     def __del__(self):
         try:
             if self._h:

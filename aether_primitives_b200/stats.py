@@ -58,3 +58,20 @@ def allreduce(values: dict, group=None) -> dict:
     dist.all_reduce(ints, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(flts, op=dist.ReduceOp.SUM, group=group)
     return {"bit_errors": int(ints[0]), "n_bits": int(ints[1]), "err_pow": float(flts[0]), "ref_pow": float(flts[1])}
+
+
+class VecStats:
+    """Result of `DeviceVec.vec_stats()` / `DeviceF32.vec_stats()` — the reference's README TODO
+    "VecStats (f32,cf32): Min(index), Max(index), Mean(index), Power" (README.md:90-92).  cf32 elements
+    are ranked by `norm_sqr`; `min`/`max` are `(value, index)` or None when nothing is comparable."""
+
+    def __init__(self, raw, complex_input: bool):
+        self.n = int(raw.n)
+        self.min = (float(raw.min_val), int(raw.min_idx)) if raw.min_idx < raw.n else None
+        self.max = (float(raw.max_val), int(raw.max_idx)) if raw.max_idx < raw.n else None
+        self.sum = complex(raw.sum_re, raw.sum_im) if complex_input else float(raw.sum_re)
+        self.mean = self.sum / self.n
+        self.power = float(raw.sum_pow) / self.n
+
+    def __repr__(self):
+        return "VecStats(n=%d, min=%r, max=%r, mean=%r, power=%r)" % (self.n, self.min, self.max, self.mean, self.power)

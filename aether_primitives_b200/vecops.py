@@ -128,6 +128,14 @@ class DeviceVec:
         """util::file::binary_writer::<cf32> (src/util/file.rs:72-107)."""
         call("ae_vec_write_raw", self._h, path.encode())
 
+    def vec_stats(self):
+        """VecStats over the vector (pending VecOps are flushed first); see `stats.VecStats`."""
+        from .stats import VecStats
+
+        raw = _lib.VecStatsRaw()
+        call("ae_vec_stats", self._h, C.byref(raw))
+        return VecStats(raw, True)
+
     def view(self, start: int, stop: int) -> "DeviceVec":  # &mut v[start..stop]
         if stop < start:
             raise _lib.AeError(_lib.AE_EIDX, "slice index starts at %d but ends at %d" % (start, stop))

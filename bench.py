@@ -297,8 +297,10 @@ def extras(torch, ae, d_in, frames, hbm_peak, steps=5, warmup=3):
     sigv = ae.DeviceVec.zeros(FFT_LEN)
     t = timed(torch, lambda: ae.spectral.correlate(d_in, sigv, fft, ae.Scale.SN, howmany=frames), steps, warmup) / steps
     rec("correlator1024", 16.0 * n, t, n, "samples")
-    # config 5: OFDM-like chain, 2048-pt, 2^16 frames, counters only
-    fr = 1 << 16
+    t = timed(torch, lambda: d_in.vec_stats(), steps, warmup) / steps
+    rec("vecstats_cf32", 8.0 * n, t, n, "samples")
+    # config 5: OFDM-like chain, 2048-pt, 2^18 frames, counters only
+    fr = 1 << 18
     t = timed(torch, lambda: ae.chain.ofdm_chain(2048, fr, 0, 0.05, 5, st), steps, warmup) / steps
     out["ofdm2048_chain"] = {"ms": t * 1e3, "Gsymbols/s": fr * 2048 / t / 1e9, "bytes_note": "counters only; compute-bound by construction"}
     return out
@@ -460,7 +462,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         from aether_primitives_b200.sharding import frame_range
         from aether_primitives_b200.stats import DeviceStats, allreduce, evm_db
 
-        total_frames = (1 << 16) * world
+        total_frames = (1 << 18) * world                      # 2^18 frames per GPU
         f0, f1 = frame_range(total_frames, rank, world)
         st = DeviceStats()
         ofdm = lambda: ae.chain.ofdm_chain(2048, f1 - f0, f0, 0.5, 5, st, None, None, ae.COMPAT_CORRECTED)

@@ -196,6 +196,18 @@ ae_status ae_stats_read(const ae_stats* device_stats, ae_stats* host);  /* synch
 ae_status ae_count_bit_errors(ae_bits* a, ae_bits* b, ae_stats* device_stats);
 ae_status ae_evm_accumulate(ae_vec* actual, ae_vec* reference, ae_stats* device_stats);
 
+/* VecStats, the README TODO "Add VecStats (f32,cf32): Min(index), Max(index), Mean(index), Power"
+ * (README.md:90-92; no definition exists in the reference, so this IS the definition):
+ * cf32 elements are ranked by norm_sqr = re*re + im*im (f32, unfused), f32 elements by value; ties keep
+ * the first index, NaN never wins, min_idx = max_idx = n when nothing is comparable; sums are f64
+ * (mean = sum/n, power = sum_pow/n).  One pass over the vector; synchronises.  Empty input: AE_ELEN. */
+typedef struct ae_vecstats {
+  uint64_t n, min_idx, max_idx;
+  float min_val, max_val;
+  double sum_re, sum_im, sum_pow;
+} ae_vecstats;
+ae_status ae_vec_stats(ae_vec* v, ae_vecstats* host_out);
+
 /* ---- fused chains ----------------------------------------------------------------------- */
 /* examples/modem.rs:15-32 in one pass: modulate -> Awgn::apply -> demod_naive (+ bit errors);
  * symbols never touch HBM.  bits_out is overwritten (len = bits_in.len). */
@@ -226,6 +238,7 @@ ae_status ae_f32_free(ae_f32* v);
 size_t    ae_f32_len(const ae_f32* v);
 ae_status ae_f32_device_ptr(ae_f32* v, void** ptr);
 ae_status ae_f32_download(ae_f32* v, float* host, size_t n);
+ae_status ae_f32_stats(ae_f32* v, ae_vecstats* host_out);   /* sum_im = 0 */
 /* compute core of util::plot::waterfall / spectrum (src/util/plot.rs:46-68, :109-130): symbols are
  * zero padded to a multiple of fft.len(); per chunk vec_rfft(Scale::SN) -> vec_mirror -> c.norm() ->
  * DB::from(..).db() when use_db (src/util/mod.rs:26-34).  levels is resized to chunks*len. */

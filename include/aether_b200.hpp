@@ -129,6 +129,12 @@ class DeviceVec {
   DeviceVec& vec_ifft(Scale s, Compat c = Compat::Reference) { check(ae_vec_ifft(h_, s.kind, s.x, (int)c)); return *this; }
   inline DeviceVec& vec_rfft(Cfft& fft, Scale s);
   inline DeviceVec& vec_rifft(Cfft& fft, Scale s);
+  /// VecStats (README.md:90-92 TODO): min/max by norm_sqr with their indices, f64 sums; mean = sum/n
+  ae_vecstats vec_stats() const {
+    ae_vecstats st;
+    check(ae_vec_stats(h_, &st));
+    return st;
+  }
   ae_vec* raw() const { return h_; }
 
  private:

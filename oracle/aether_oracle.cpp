@@ -708,4 +708,43 @@ int ora_correlate(ocf32* data, size_t n, size_t frames, const ocf32* sig, size_t
   return ORA_OK;
 }
 
+// VecStats (README.md:90-92 TODO; the reference has no definition, so this restates the product's):
+// rank cf32 by norm_sqr = re*re + im*im (f32, unfused), f32 by value; first index wins ties, NaN never
+// wins, idx = n when nothing is comparable; f64 sums.  out = {n, min_idx, max_idx}, vals = {min, max},
+// sums = {sum_re, sum_im, sum_pow}.
+static void ora_stats_any(const float* p, size_t n, int cplx, uint64_t* out, float* vals, double* sums) {
+  uint64_t imn = n, imx = n;
+  float mn = 0.f, mx = 0.f;
+  double sre = 0, sim = 0, spw = 0;
+  for (size_t i = 0; i < n; ++i) {
+    float v;
+    if (cplx) {
+      const float re = p[2 * i], im = p[2 * i + 1];
+      const float a = re * re, b = im * im;
+      v = a + b;
+      sre += re; sim += im; spw += (double)re * re + (double)im * im;
+    } else {
+      v = p[i];
+      sre += v; spw += (double)v * v;
+    }
+    if (v == v) {
+      if (imn == n || v < mn) { mn = v; imn = i; }
+      if (imx == n || v > mx) { mx = v; imx = i; }
+    }
+  }
+  out[0] = n; out[1] = imn; out[2] = imx;
+  vals[0] = mn; vals[1] = mx;
+  sums[0] = sre; sums[1] = sim; sums[2] = spw;
+}
+int ora_vec_stats(const ocf32* v, size_t n, uint64_t* out, float* vals, double* sums) {
+  if (n == 0) return ORA_ELEN;
+  ora_stats_any((const float*)v, n, 1, out, vals, sums);
+  return ORA_OK;
+}
+int ora_f32_stats(const float* v, size_t n, uint64_t* out, float* vals, double* sums) {
+  if (n == 0) return ORA_ELEN;
+  ora_stats_any(v, n, 0, out, vals, sums);
+  return ORA_OK;
+}
+
 }  // extern "C"

@@ -61,6 +61,8 @@ def lib():
         l.ora_ofdm_chain.argtypes = [C.c_size_t, C.c_size_t, C.c_uint64, C.c_float, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
         l.ora_spectrogram.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+        l.ora_vec_stats.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.ora_f32_stats.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         l.ora_correlate.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_int]
         _lib = l
     return _lib
@@ -274,3 +276,17 @@ def correlate(data, n, sig, scale_kind=SCALE_NONE, scale_x=1.0, compat=REFERENCE
     data, sig = c64(data), c64(sig)
     _ck(lib().ora_correlate(_p(data), n, data.size // n, _p(sig), sig.size, scale_kind, float(scale_x), compat))
     return data
+
+
+def vec_stats(v):
+    """-> dict(n, min_idx, max_idx, min_val, max_val, sum_re, sum_im, sum_pow); complex64 or float32 input."""
+    v = np.ascontiguousarray(v)
+    cplx = np.iscomplexobj(v)
+    v = c64(v) if cplx else np.ascontiguousarray(v, dtype=np.float32)
+    out = np.zeros(3, np.uint64)
+    vals = np.zeros(2, np.float32)
+    sums = np.zeros(3, np.float64)
+    fn = lib().ora_vec_stats if cplx else lib().ora_f32_stats
+    _ck(fn(_p(v), v.size, _p(out), _p(vals), _p(sums)))
+    return dict(n=int(out[0]), min_idx=int(out[1]), max_idx=int(out[2]), min_val=float(vals[0]), max_val=float(vals[1]),
+                sum_re=float(sums[0]), sum_im=float(sums[1]), sum_pow=float(sums[2]))
