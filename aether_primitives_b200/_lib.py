@@ -37,6 +37,11 @@ class VecStatsRaw(C.Structure):
                 ("sum_re", C.c_double), ("sum_im", C.c_double), ("sum_pow", C.c_double)]
 
 
+class PipeStage(C.Structure):
+    _fields_ = [("name", C.c_char * 16), ("processed", C.c_uint64), ("active_ms", C.c_double), ("elapsed_ms", C.c_double),
+                ("per_second", C.c_double), ("utilisation_pct", C.c_double)]
+
+
 _P = C.c_void_p
 _SZ = C.c_size_t
 _I = C.c_int
@@ -138,6 +143,12 @@ _SIGS = {
     "ae_chain_destroy": (None, [_P]),
     "ae_chain_exec": (None, [_P, _P, _P]),
     "ae_chain_exec_host": (None, [_P, _P, _SZ, _P]),
+    "ae_pipe_create": (None, [_P, _SZ, _I, C.POINTER(_P)]),
+    "ae_pipe_destroy": (None, [_P]),
+    "ae_pipe_send": (None, [_P, _P, _P]),
+    "ae_pipe_recv": (None, [_P, C.POINTER(_P)]),
+    "ae_pipe_in_flight": (_SZ, [_P]),
+    "ae_pipe_report": (None, [_P, C.POINTER(PipeStage), _I]),
     "ae_chain_exec_unfused": (None, [_P, _P, _P, _P]),
     "ae_ofdm_chain": (None, [_SZ, _SZ, _U64, _F, _U64, _I, _P, _P, _P]),
     "ae_f32_alloc": (None, [_SZ, C.POINTER(_P)]),

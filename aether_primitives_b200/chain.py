@@ -55,3 +55,43 @@ def ofdm_chain(fft_len: int, frames: int, first_frame_id: int, noise_power: floa
                compat: int = _lib.COMPAT_REFERENCE) -> None:
     call("ae_ofdm_chain", fft_len, frames, C.c_uint64(first_frame_id), C.c_float(noise_power), C.c_uint64(noise_seed), compat,
          tx_bits._h if tx_bits is not None else None, rx_bits._h if rx_bits is not None else None, stats._h if stats is not None else None)
+
+
+class ChainPipeline:
+    """Streaming form of `FftFirDemod.run_host` — the analogue of the reference's thread pipeline and
+    buffer pool (src/pipeline.rs:26-137, src/pool.rs:43-130) for this path: `send` queues one block of
+    `block_frames` frames (H2D copy -> fused kernel -> D2H copy on one of `depth` buffer slots) and returns
+    at once; `recv` returns the address of the next finished bit buffer, in order; `report` gives what
+    each reference stage prints once a second (processed, active time, rate, utilisation)."""
+
+    def __init__(self, chain: FftFirDemod, block_frames: int, depth: int = 3):
+        h = C.c_void_p()
+        call("ae_pipe_create", chain._h, block_frames, depth, C.byref(h))
+        self._h = h
+        self._chain = chain              # the pipe borrows the chain's window / taps
+        self.block_frames = block_frames
+
+    def send(self, host_in_ptr: int, host_bits_ptr: int) -> None:
+        call("ae_pipe_send", self._h, C.c_void_p(host_in_ptr), C.c_void_p(host_bits_ptr))
+
+    def recv(self) -> int:
+        p = C.c_void_p()
+        call("ae_pipe_recv", self._h, C.byref(p))
+        return p.value or 0
+
+    def in_flight(self) -> int:
+        return int(_lib.lib().ae_pipe_in_flight(self._h))
+
+    def report(self, reset: bool = False) -> list[dict]:
+        st = (_lib.PipeStage * 3)()
+        call("ae_pipe_report", self._h, st, int(reset))
+        return [dict(name=s.name.decode(), processed=int(s.processed), active_ms=s.active_ms, elapsed_ms=s.elapsed_ms,
+                     per_second=s.per_second, utilisation_pct=s.utilisation_pct) for s in st]
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().ae_pipe_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

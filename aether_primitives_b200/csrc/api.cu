@@ -1388,6 +1388,156 @@ ae_status ae_chain_exec_host(ae_chain* ch, const ae_cf32* host_in, size_t n_samp
   return AE_OK;
 }
 
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// Streaming form of the host pipeline: the src/pipeline.rs:26-137 + src/pool.rs:43-130 analogue for
+// the one place this path has stages.  Stages are the copy engines and the SMs instead of threads;
+// the "pool" is a ring of `depth` slots (device input block, device bit block, stream, events), and
+// the per-stage report (processed, active time, rate, utilisation: pipeline.rs:93-107) comes from
+// CUDA events: a stage's active time is the union of its [start, end] intervals.
+// -------------------------------------------------------------------------------------------------
+struct PipeSlot {
+  cudaStream_t st = nullptr;
+  float2* d_in = nullptr;
+  uint8_t* d_out = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // before H2D, after H2D, after kernel, after D2H
+  uint8_t* host_bits = nullptr;
+  bool busy = false;
+};
+struct ae_pipe {
+  ae_chain* ch;
+  size_t block_frames;
+  std::vector<PipeSlot> slots;
+  std::vector<uint8_t*> done;          // retired blocks not yet handed out by ae_pipe_recv (FIFO)
+  size_t head = 0, tail = 0;           // next slot to send into / oldest slot in flight
+  cudaEvent_t t0 = nullptr;            // time origin of the current report window
+  double active_ms[3] = {0, 0, 0}, last_end_ms[3] = {0, 0, 0}, window_end_ms = 0;
+  uint64_t processed = 0;
+};
+
+namespace {
+ae_status pipe_retire(ae_pipe* p, PipeSlot& s) {
+  CK(cudaEventSynchronize(s.ev[3]));
+  float t[4];
+  for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&t[i], p->t0, s.ev[i]));
+  for (int k = 0; k < 3; ++k) {
+    const double start = std::max((double)t[k], p->last_end_ms[k]), end = t[k + 1];
+    if (end > start) p->active_ms[k] += end - start;
+    p->last_end_ms[k] = std::max(p->last_end_ms[k], end);
+  }
+  p->window_end_ms = std::max(p->window_end_ms, (double)t[3]);
+  p->processed += 1;
+  p->done.push_back(s.host_bits);
+  s.busy = false;
+  p->tail += 1;
+  return AE_OK;
+}
+}  // namespace
+
+extern "C" {
+
+ae_status ae_pipe_create(ae_chain* ch, size_t block_frames, int depth, ae_pipe** out) {
+  if (!ch || !out) return fail(AE_EARG, "null");
+  if (!ch->fused) return fail(AE_EARG, "host pipeline needs the fused chain (power-of-two FFT length 256..4096)");
+  if (block_frames == 0 || depth < 1 || depth > 16) return fail(AE_EARG, "block_frames >= 1 and 1 <= depth <= 16");
+  cudaSetDevice(ch->c->dev);
+  TRY(ae_sync());                      // the chain's window/taps uploads are ordered on the context stream
+  ae_pipe* p = new ae_pipe;
+  p->ch = ch;
+  p->block_frames = block_frames;
+  p->slots.resize(depth);
+  cudaError_t e = cudaEventCreate(&p->t0);
+  for (auto& s : p->slots) {
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s.d_in, block_frames * ch->n * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s.d_out, block_frames * ch->n * 2);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&s.ev[i]);
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(p->t0, p->slots[0].st);
+  if (e != cudaSuccess) {
+    ae_pipe_destroy(p);
+    return fail(e == cudaErrorMemoryAllocation ? AE_EOOM : AE_ECUDA, std::string("ae_pipe_create: ") + cudaGetErrorString(e));
+  }
+  *out = p;
+  return AE_OK;
+}
+
+ae_status ae_pipe_destroy(ae_pipe* p) {
+  if (!p) return AE_OK;
+  cudaSetDevice(p->ch->c->dev);
+  for (auto& s : p->slots) {
+    if (s.st) cudaStreamSynchronize(s.st);
+    for (auto& ev : s.ev) if (ev) cudaEventDestroy(ev);
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.st) cudaStreamDestroy(s.st);
+  }
+  if (p->t0) cudaEventDestroy(p->t0);
+  delete p;
+  return AE_OK;
+}
+
+ae_status ae_pipe_send(ae_pipe* p, const ae_cf32* host_in, uint8_t* host_bits) {
+  if (!p || !host_in || !host_bits) return fail(AE_EARG, "null");
+  ae_chain* ch = p->ch;
+  cudaSetDevice(ch->c->dev);
+  PipeSlot& s = p->slots[p->head % p->slots.size()];
+  if (s.busy) TRY(pipe_retire(p, s));  // every slot in flight: wait for the oldest block (Pool::take on an empty pool)
+  const size_t ns = p->block_frames * ch->n;
+  CK(cudaEventRecord(s.ev[0], s.st));
+  CK(cudaMemcpyAsync(s.d_in, host_in, ns * sizeof(float2), cudaMemcpyHostToDevice, s.st));
+  CK(cudaEventRecord(s.ev[1], s.st));
+  launch_chain_fused(s.d_in, s.d_out, ch->n, p->block_frames, ch->d_window, ch->d_taps, ch->ntaps, ch->d_tw,
+                     ch->compat == AE_COMPAT_REFERENCE, ch->s, ch->compat, s.st);
+  CKL(1);
+  CK(cudaEventRecord(s.ev[2], s.st));
+  CK(cudaMemcpyAsync(host_bits, s.d_out, ns * 2, cudaMemcpyDeviceToHost, s.st));
+  CK(cudaEventRecord(s.ev[3], s.st));
+  s.host_bits = host_bits;
+  s.busy = true;
+  p->head += 1;
+  return AE_OK;
+}
+
+ae_status ae_pipe_recv(ae_pipe* p, uint8_t** host_bits_done) {
+  if (!p || !host_bits_done) return fail(AE_EARG, "null");
+  cudaSetDevice(p->ch->c->dev);
+  if (p->done.empty()) {
+    if (p->tail == p->head) return fail(AE_EARG, "ae_pipe_recv: nothing in flight");
+    TRY(pipe_retire(p, p->slots[p->tail % p->slots.size()]));
+  }
+  *host_bits_done = p->done.front();
+  p->done.erase(p->done.begin());
+  return AE_OK;
+}
+
+size_t ae_pipe_in_flight(const ae_pipe* p) { return p ? (p->head - p->tail) + p->done.size() : 0; }
+
+ae_status ae_pipe_report(ae_pipe* p, ae_pipe_stage stages[3], int reset) {
+  if (!p || !stages) return fail(AE_EARG, "null");
+  static const char* names[3] = {"h2d", "fft-fir-demod", "d2h"};
+  for (int k = 0; k < 3; ++k) {
+    ae_pipe_stage& r = stages[k];
+    memset(&r, 0, sizeof(r));
+    snprintf(r.name, sizeof(r.name), "%s", names[k]);
+    r.processed = p->processed;
+    r.active_ms = p->active_ms[k];
+    r.elapsed_ms = p->window_end_ms;
+    r.per_second = p->window_end_ms > 0 ? p->processed / p->window_end_ms * 1e3 : 0.0;
+    r.utilisation_pct = p->window_end_ms > 0 ? 100.0 * p->active_ms[k] / p->window_end_ms : 0.0;
+  }
+  if (reset) {
+    if (p->tail != p->head) return fail(AE_EARG, "ae_pipe_report(reset): blocks still in flight");
+    cudaSetDevice(p->ch->c->dev);
+    CK(cudaEventRecord(p->t0, p->slots[0].st));
+    for (int k = 0; k < 3; ++k) p->active_ms[k] = p->last_end_ms[k] = 0;
+    p->window_end_ms = 0;
+    p->processed = 0;
+  }
+  return AE_OK;
+}
+
 ae_status ae_ofdm_chain(size_t fft_len, size_t frames, uint64_t first_frame_id, float noise_power, uint64_t noise_seed,
                         int compat, ae_bits* tx_bits, ae_bits* rx_bits, ae_stats* d) {
   if (!ofdm_supported(fft_len)) return fail(AE_EARG, "ofdm chain supports power-of-two FFT lengths 512..4096");

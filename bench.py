@@ -447,6 +447,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         # the host path must give the same bits as the device path
         same = bool(torch.equal(h_out.cuda(), bits[: 2 * ne]))
         e2e["matches_device_path"] = same
+        # yard-stick: a bare pinned-host -> device copy of the same input buffer (the PCIe ceiling of e2e)
+        d_tmp = torch.empty(ne, dtype=torch.complex64, device="cuda")
+        d_tmp.copy_(h_in, non_blocking=True)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            d_tmp.copy_(h_in, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d = 3 * 8 * ne / (c0.elapsed_time(c1) / 1e3) / 1e9
+        e2e["h2d_copy_GB/s"] = h2d
+        e2e["frac_of_h2d_copy"] = (8 * ne * e_steps / e_secs / 1e9) / h2d
+        del d_tmp
         del h_in, h_out
         try:
             os.sched_setaffinity(0, affinity0)       # the CPU baseline below uses every host core

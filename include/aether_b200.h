@@ -222,6 +222,27 @@ ae_status ae_chain_exec(ae_chain* c, ae_vec* in, ae_bits* bits_out);    /* bits_
 /* same with HOST buffers: chunked H2D -> kernel -> D2H pipeline on internal streams */
 ae_status ae_chain_exec_host(ae_chain* c, const ae_cf32* host_in, size_t n_samples,
                              uint8_t* host_bits);
+/* Streaming form of the same pipeline — the analogue of src/pipeline.rs:26-137 (stages connected by
+ * channels, a report per stage: processed / active time / rate / utilisation, :93-107) and of
+ * src/pool.rs:43-130 (a pool of reusable buffers) for this path: the stages are H2D copy, the fused
+ * kernel and D2H copy; the pool is a ring of `depth` device buffer slots.  ae_pipe_send queues one
+ * block of block_frames frames and returns at once (when every slot is in flight it first waits for
+ * the oldest block, like taking from an empty pool); ae_pipe_recv hands back, in order, the
+ * host_bits pointer of the next finished block (waiting for it if necessary).  Host buffers should
+ * be pinned (ae_host_alloc) and must stay valid until received. */
+typedef struct ae_pipe ae_pipe;
+typedef struct ae_pipe_stage {
+  char name[16];
+  uint64_t processed;                 /* blocks since the last reset */
+  double active_ms, elapsed_ms;       /* union of the stage's busy intervals / report window */
+  double per_second, utilisation_pct;
+} ae_pipe_stage;
+ae_status ae_pipe_create(ae_chain* c, size_t block_frames, int depth, ae_pipe** out);
+ae_status ae_pipe_destroy(ae_pipe* p);
+ae_status ae_pipe_send(ae_pipe* p, const ae_cf32* host_in, uint8_t* host_bits);
+ae_status ae_pipe_recv(ae_pipe* p, uint8_t** host_bits_done);
+size_t    ae_pipe_in_flight(const ae_pipe* p);      /* sent and not yet received */
+ae_status ae_pipe_report(ae_pipe* p, ae_pipe_stage stages[3], int reset);
 /* unfused composition of the same chain from the stand-alone kernels (for cross-checking) */
 ae_status ae_chain_exec_unfused(ae_chain* c, ae_vec* in, ae_bits* bits_out, ae_vec* symbols_out);
 

@@ -247,4 +247,48 @@ inline DeviceBits generate(const std::vector<uint8_t>& init, const std::vector<u
 }
 }  // namespace sequence
 
+/// headline chain: per frame Cfft::fwd(scale) -> FIR (zero state per frame) -> QPSK demod_naive, one kernel
+class FftFirDemod {
+ public:
+  FftFirDemod(size_t fft_len, const std::vector<cf32>& taps, Scale s, Compat c = Compat::Reference) {
+    check(ae_chain_create(fft_len, reinterpret_cast<const ae_cf32*>(taps.data()), taps.size(), s.kind, s.x, (int)c, &h_));
+  }
+  FftFirDemod(const FftFirDemod&) = delete;
+  ~FftFirDemod() { ae_chain_destroy(h_); }
+  void run(const DeviceVec& in, DeviceBits& bits_out) { check(ae_chain_exec(h_, in.raw(), bits_out.raw())); }
+  /// host buffers (ideally from ae_host_alloc): chunked H2D -> kernel -> D2H inside the call
+  void run_host(const cf32* host_in, size_t n_samples, uint8_t* host_bits) {
+    check(ae_chain_exec_host(h_, reinterpret_cast<const ae_cf32*>(host_in), n_samples, host_bits));
+  }
+  ae_chain* raw() const { return h_; }
+
+ private:
+  ae_chain* h_ = nullptr;
+};
+
+/// pipeline::Pipeline / pool::Pool analogue for this path (src/pipeline.rs:26-137, src/pool.rs:43-130):
+/// send() queues a block on one of `depth` buffer slots, recv() returns finished bit buffers in order,
+/// report() is the per-stage line the reference prints (processed, active time, rate, utilisation).
+class ChainPipeline {
+ public:
+  ChainPipeline(FftFirDemod& chain, size_t block_frames, int depth = 3) { check(ae_pipe_create(chain.raw(), block_frames, depth, &h_)); }
+  ChainPipeline(const ChainPipeline&) = delete;
+  ~ChainPipeline() { ae_pipe_destroy(h_); }
+  void send(const cf32* host_in, uint8_t* host_bits) { check(ae_pipe_send(h_, reinterpret_cast<const ae_cf32*>(host_in), host_bits)); }
+  uint8_t* recv() {
+    uint8_t* p = nullptr;
+    check(ae_pipe_recv(h_, &p));
+    return p;
+  }
+  size_t in_flight() const { return ae_pipe_in_flight(h_); }
+  std::vector<ae_pipe_stage> report(bool reset = false) {
+    std::vector<ae_pipe_stage> st(3);
+    check(ae_pipe_report(h_, st.data(), reset));
+    return st;
+  }
+
+ private:
+  ae_pipe* h_ = nullptr;
+};
+
 }  // namespace aether

@@ -104,6 +104,38 @@ int main() {
     m.demod_naive(sym, rx, Compat::Corrected);
     if (rx.to_host() != b) { std::printf("FAIL modem loop-back\n"); return 1; }
   }
+  {  // headline chain: device call, streamed host blocks (pipeline.rs / pool.rs analogue) and VecStats agree
+    const size_t n = 1024, block = 8, blocks = 5;
+    std::vector<cf32> taps(64), x(n * block * blocks);
+    for (size_t k = 0; k < taps.size(); ++k) taps[k] = cf32(1.f / (1.f + k), 0.01f * k);
+    uint32_t lcg = 12345;
+    for (auto& e : x) {
+      lcg = lcg * 1664525u + 1013904223u; const float re = (float)(lcg >> 8) / 8388608.f - 1.f;
+      lcg = lcg * 1664525u + 1013904223u; const float im = (float)(lcg >> 8) / 8388608.f - 1.f;
+      e = cf32(re, im);
+    }
+    FftFirDemod chain(n, taps, Scale::SN());
+    DeviceVec dx(x);
+    DeviceBits want(2 * x.size());
+    chain.run(dx, want);
+    const std::vector<uint8_t> w = want.to_host();
+    ChainPipeline pipe(chain, block, 2);
+    std::vector<uint8_t> got(2 * x.size());
+    for (size_t b = 0; b < blocks; ++b) pipe.send(x.data() + b * block * n, got.data() + 2 * b * block * n);
+    for (size_t b = 0; b < blocks; ++b)
+      if (pipe.recv() != got.data() + 2 * b * block * n) { std::printf("FAIL pipeline order\n"); return 1; }
+    if (got != w) { std::printf("FAIL pipeline bits\n"); return 1; }
+    const auto rep = pipe.report();
+    if (rep[1].processed != blocks || rep[1].utilisation_pct <= 0) { std::printf("FAIL pipeline report\n"); return 1; }
+    const ae_vecstats st = dx.vec_stats();
+    size_t imax = 0;
+    float vmax = -1.f;
+    for (size_t i = 0; i < x.size(); ++i) {
+      const float a = x[i].real() * x[i].real(), b2 = x[i].imag() * x[i].imag(), v = a + b2;
+      if (v > vmax) { vmax = v; imax = i; }
+    }
+    if (st.n != x.size() || st.max_idx != imax || st.max_val != vmax) { std::printf("FAIL vec_stats\n"); return 1; }
+  }
   sync();
   std::printf("host mirror ok\n");
   return 0;

@@ -204,3 +204,48 @@ def test_ofdm_chain_vs_oracle(ae, n):
     ae.chain.ofdm_chain(n, 5, 0, 0.3, 5, None, None, lo)
     ae.chain.ofdm_chain(n, 3, 5, 0.3, 5, None, None, hi)
     assert np.concatenate([lo.to_numpy(), hi.to_numpy()]).tolist() == whole.to_numpy().tolist()
+
+
+def test_streaming_pipeline_matches_device_path_and_reports_stages(ae):
+    """ae_pipe_* (pipeline.rs / pool.rs analogue): blocks streamed through depth-3 slots give the device
+    path's bits, in order; the per-stage report counts every block and keeps utilisation within 0..100 %."""
+    import torch
+    from aether_primitives_b200.chain import ChainPipeline, FftFirDemod
+
+    n, block_frames, blocks = 1024, 256, 11
+    rng = np.random.default_rng(77)
+    taps = (rng.standard_normal(64) + 1j * rng.standard_normal(64)).astype(np.complex64) / 8
+    x = (rng.standard_normal(blocks * block_frames * n) + 1j * rng.standard_normal(blocks * block_frames * n)).astype(np.complex64)
+    ch = FftFirDemod(n, taps)
+    want = ae.DeviceBits.with_capacity(2 * x.size)
+    ch.run(ae.DeviceVec.from_numpy(x), want)
+    want = want.to_numpy()
+
+    h_in = torch.from_numpy(x).pin_memory()
+    h_out = torch.zeros(2 * x.size, dtype=torch.uint8).pin_memory()
+    pipe = ChainPipeline(ch, block_frames, depth=3)
+    with pytest.raises(ae.AeError):
+        pipe.recv()                                           # nothing in flight
+    bs, bo = block_frames * n * 8, block_frames * n * 2
+    received = []
+    for b in range(blocks):                                    # more blocks than slots: send() recycles the oldest slot
+        pipe.send(h_in.data_ptr() + b * bs, h_out.data_ptr() + b * bo)
+    assert pipe.in_flight() == blocks
+    for b in range(blocks):
+        received.append(pipe.recv())
+    assert received == [h_out.data_ptr() + b * bo for b in range(blocks)]
+    assert pipe.in_flight() == 0
+    assert np.array_equal(h_out.numpy(), want)
+    rep = pipe.report(reset=True)
+    assert [r["name"] for r in rep] == ["h2d", "fft-fir-demod", "d2h"]
+    for r in rep:
+        assert r["processed"] == blocks and 0.0 < r["utilisation_pct"] <= 100.0 + 1e-6 and r["per_second"] > 0
+        assert r["active_ms"] <= r["elapsed_ms"] + 1e-6
+    assert all(r["processed"] == 0 for r in pipe.report())
+    # a second window after the reset works and interleaved send/recv keeps order
+    for b in range(4):
+        pipe.send(h_in.data_ptr() + b * bs, h_out.data_ptr() + b * bo)
+        assert pipe.recv() == h_out.data_ptr() + b * bo
+    assert pipe.report()[1]["processed"] == 4
+    with pytest.raises(ae.AeError):
+        ChainPipeline(ch, 0)
