@@ -69,3 +69,19 @@ def test_scale_factor_host_entry_point():
         assert ae.Scale.SN.factor(n) == o.scale_factor(o.SCALE_SN, n)
         assert ae.Scale.N.factor(n) == o.scale_factor(o.SCALE_N, n)
     assert ae.Scale.X(2.5).factor(7) == 2.5
+
+
+def test_rust_sys_binding_is_generated_from_the_current_header():
+    """rust/aether-b200-sys/src/lib.rs is emitted by tools/gen_rust_sys.py; it must match the header
+    (no Rust toolchain here, so this is the only guard against drift) and declare every export."""
+    import re
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    from aether_primitives_b200 import _lib
+
+    text = open(os.path.join(root, "rust", "aether-b200-sys", "src", "lib.rs")).read()
+    assert set(re.findall(r"pub fn (ae_\w+)\(", text)) == set(_lib.EXPORTS)
