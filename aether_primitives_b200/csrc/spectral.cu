@@ -10,11 +10,16 @@
 
 namespace ae {
 
-template <int N>
+// CTA shape: TH threads (more when one frame needs them).  The spectrogram runs ONE transform per frame
+// and is latency-bound at 16 warps/SM: 256-thread CTAs at <= 64 registers (32 warps/SM) measured
+// 382 vs 318 Gsamples/s.  The correlator keeps two transforms' worth of state and is faster with
+// 128-thread CTAs at <= 128 registers (262 vs 243 Gsamples/s).
+template <int N, int TH>
 struct SpecLaunch {
   static constexpr int T = FftCfg<N>::T;
-  static constexpr int F = T >= 128 ? 1 : (128 / T);
+  static constexpr int F = T >= TH ? 1 : (TH / T);
   static constexpr int THREADS = F * T;
+  static constexpr int MINB = THREADS <= 256 ? 4 : (THREADS <= 512 ? 2 : 1);
   static constexpr size_t SMEM = (size_t)F * FftCfg<N>::SMEM_ELEMS * sizeof(float2);
 };
 
@@ -30,11 +35,11 @@ __device__ __forceinline__ float level_of(float2 y, int use_db) {
 }
 
 template <int N, bool INV>
-__global__ void __launch_bounds__(SpecLaunch<N>::THREADS, SpecLaunch<N>::THREADS <= 128 ? 4 : 2)
+__global__ void __launch_bounds__(SpecLaunch<N, 256>::THREADS, SpecLaunch<N, 256>::MINB)
 spectrogram_kernel(const float2* __restrict__ in, size_t n_samples, float* __restrict__ levels, const float2* __restrict__ tw,
                    size_t frames, float scale, int use_db) {
   using C = FftCfg<N>;
-  using LC = SpecLaunch<N>;
+  using LC = SpecLaunch<N, 256>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* smem = reinterpret_cast<float2*>(smem_raw);
   const int f = threadIdx.x / C::T;
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(256) levels_kernel(const float2* __restrict__ 
 template <int N>
 static void launch_spec_n(const float2* in, size_t n_samples, float* levels, const float2* tw, size_t frames, bool inverse, float scale,
                           int use_db, cudaStream_t st) {
-  using LC = SpecLaunch<N>;
+  using LC = SpecLaunch<N, 256>;
   const size_t want = (frames + LC::F - 1) / LC::F;
   auto launch = [&](auto kern) {
     if (LC::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
@@ -111,11 +116,11 @@ void launch_levels(const float2* spec, float* levels, size_t total, size_t n, in
 // FWD_INV: exponent sign of Cfft::fwd is + (compat=reference); the backward transform uses the other.
 // -------------------------------------------------------------------------------------------------
 template <int N, bool FWD_INV>
-__global__ void __launch_bounds__(SpecLaunch<N>::THREADS, SpecLaunch<N>::THREADS <= 128 ? 4 : 2)
+__global__ void __launch_bounds__(SpecLaunch<N, 128>::THREADS, SpecLaunch<N, 128>::MINB)
 correlate_kernel(float2* __restrict__ data, const float2* __restrict__ sig, const float2* __restrict__ tw, size_t frames, float scale,
                  int do_scale) {
   using C = FftCfg<N>;
-  using LC = SpecLaunch<N>;
+  using LC = SpecLaunch<N, 128>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* sm = reinterpret_cast<float2*>(smem_raw) + (threadIdx.x / C::T) * C::SMEM_ELEMS;
   const int f = threadIdx.x / C::T;
@@ -145,7 +150,7 @@ correlate_kernel(float2* __restrict__ data, const float2* __restrict__ sig, cons
 template <int N>
 static void launch_corr_n(float2* data, const float2* sig, const float2* tw, size_t frames, bool fwd_inverse, float scale, int do_scale,
                           cudaStream_t st) {
-  using LC = SpecLaunch<N>;
+  using LC = SpecLaunch<N, 128>;
   const size_t want = (frames + LC::F - 1) / LC::F;
   auto launch = [&](auto kern) {
     if (LC::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
