@@ -309,76 +309,210 @@ __global__ void __launch_bounds__(256) fft_generic_pass_kernel(const float2* __r
   out[frame * n + (size_t)(j - k) * p + k + (size_t)q * ns] = acc;
 }
 
-// Any length up to 6144 in ONE kernel: the frame lives in shared memory (two ping-pong buffers), one
-// Stockham pass per factor with the same per-output formula as above; persistent CTAs walk the frames.
-// This is what a batch of N = 100 transforms (the reference's own test length) runs through.
+// Any length up to 6144 in ONE kernel: the frames of a CTA live in shared memory (two ping-pong buffers,
+// padded by one cf32 per 32), one Stockham pass per factor.  The first pass reads global memory, the
+// last one writes it.  Radices 2/3/4/5/7/8/11/13 run as register butterflies (one butterfly = one
+// thread: P loads, P-1 table twiddles, P stores); any other (prime) factor falls back to one output per
+// thread with P terms.  Several frames share a CTA when the length is small (N = 100, the reference's
+// own test length: 20 frames per CTA), so all 256 threads have work in every pass.  The inverse
+// transform is conj -> forward -> conj, applied at the first load and the last store.
 constexpr int kGenSmemMaxN = 6144;
 constexpr int kGenMaxRadices = 16;
 struct GenRadices { unsigned r[kGenMaxRadices]; int count; };
 
-__global__ void __launch_bounds__(256) fft_generic_smem_kernel(const float2* __restrict__ in, float2* __restrict__ out,
-                                                               const float2* __restrict__ tw, unsigned n, size_t frames,
+__device__ __forceinline__ unsigned gen_pad(unsigned i) { return i + (i >> 5); }
+
+// forward DFT of odd prime length P on registers.  root[r] = exp(-2 pi i r / P), r = 1..(P-1)/2:
+//   X[q], X[P-q] = x0 + sum_r cos(2 pi r q / P) (x_r + x_{P-r})  -/+  i sum_r sin(2 pi r q / P) (x_r - x_{P-r})
+template <int P>
+__device__ __forceinline__ void odd_dft(float2 (&v)[P], const float2 (&root)[(P - 1) / 2 + 1]) {
+  constexpr int H = (P - 1) / 2;
+  float2 a[H + 1], b[H + 1];
+#pragma unroll
+  for (int r = 1; r <= H; ++r) { a[r] = cx_add(v[r], v[P - r]); b[r] = cx_sub(v[r], v[P - r]); }
+  float2 y0 = v[0];
+#pragma unroll
+  for (int r = 1; r <= H; ++r) y0 = cx_add(y0, a[r]);
+  float2 o[P];
+  o[0] = y0;
+#pragma unroll
+  for (int q = 1; q <= H; ++q) {
+    float2 e = v[0], f = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int r = 1; r <= H; ++r) {
+      const int idx = (r * q) % P;                       // compile-time after unrolling
+      const float c = idx <= H ? root[idx].x : root[P - idx].x;
+      const float sn = idx <= H ? -root[idx].y : root[P - idx].y;   // sin(2 pi idx / P)
+      e.x = fmaf(c, a[r].x, e.x); e.y = fmaf(c, a[r].y, e.y);
+      f.x = fmaf(sn, b[r].x, f.x); f.y = fmaf(sn, b[r].y, f.y);
+    }
+    o[q] = make_float2(e.x + f.y, e.y - f.x);            // e - i f
+    o[P - q] = make_float2(e.x - f.y, e.y + f.x);        // e + i f
+  }
+#pragma unroll
+  for (int i = 0; i < P; ++i) v[i] = o[i];
+}
+
+template <int P, bool SRC_SMEM, bool DST_SMEM>
+__device__ __forceinline__ void gen_butterfly_pass(const float2* src, float2* dst, const float2* __restrict__ tw, unsigned n, unsigned ns,
+                                                   unsigned slots, bool conj_in, bool conj_out, bool do_scale, float scale) {
+  const unsigned m = n / P, tws = n / (ns * P);
+  constexpr int H = (P - 1) / 2;
+  float2 root[H + 1];
+  if constexpr (P & 1) {
+#pragma unroll
+    for (int r = 1; r <= H; ++r) root[r] = __ldg(tw + r * m);
+  }
+  for (unsigned item = threadIdx.x; item < slots * m; item += blockDim.x) {
+    const unsigned s = item / m, j = item - s * m, k = j % ns, sb = s * n;
+    float2 v[P];
+#pragma unroll
+    for (int r = 0; r < P; ++r) {
+      const unsigned idx = sb + j + r * m;
+      v[r] = SRC_SMEM ? src[gen_pad(idx)] : ld_stream(src + idx);
+      if (conj_in) v[r].y = -v[r].y;
+    }
+    if (ns > 1) {
+#pragma unroll
+      for (int r = 1; r < P; ++r) v[r] = cx_mul(v[r], __ldg(tw + r * k * tws));   // r*k*tws < n
+    }
+    if constexpr (P & 1) odd_dft<P>(v, root);
+    else Dft<P, false>::run(v);
+    const unsigned d0 = sb + (j - k) * P + k;
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      float2 y = v[q];
+      const unsigned idx = d0 + q * ns;
+      if (DST_SMEM) {
+        dst[gen_pad(idx)] = y;
+      } else {
+        if (conj_out) y.y = -y.y;
+        if (do_scale) y = cx_scale_exact(y, scale);
+        st_stream(dst + idx, y);
+      }
+    }
+  }
+}
+
+// any radix p: one output per thread, p terms (exponent of W_n for term r: r*k*tws + ((r*q) mod p)*n/p)
+template <bool SRC_SMEM, bool DST_SMEM>
+__device__ __forceinline__ void gen_output_pass(const float2* src, float2* dst, const float2* __restrict__ tw, unsigned n, unsigned p,
+                                                unsigned ns, unsigned slots, bool conj_in, bool conj_out, bool do_scale, float scale) {
+  const unsigned m = n / p, tws = n / (ns * p), wp = n / p;
+  for (unsigned o = threadIdx.x; o < slots * n; o += blockDim.x) {
+    const unsigned s = o / n, oo = o - s * n, q = oo / m, j = oo - q * m, k = j % ns, sb = s * n;
+    float2 acc = make_float2(0.0f, 0.0f);
+    const unsigned step1 = k * tws;
+    unsigned e1 = 0, rq = 0;
+    for (unsigned r = 0; r < p; ++r) {
+      unsigned e = e1 + rq * wp;
+      if (e >= n) e -= n;
+      const float2 w = __ldg(tw + e);
+      const unsigned idx = sb + j + r * m;
+      float2 x = SRC_SMEM ? src[gen_pad(idx)] : src[idx];
+      if (conj_in) x.y = -x.y;
+      cx_fma(acc, x, w);
+      e1 += step1;
+      rq += q;
+      if (rq >= p) rq -= p;
+    }
+    const unsigned idx = sb + (j - k) * p + k + q * ns;
+    if (DST_SMEM) {
+      dst[gen_pad(idx)] = acc;
+    } else {
+      if (conj_out) acc.y = -acc.y;
+      if (do_scale) acc = cx_scale_exact(acc, scale);
+      dst[idx] = acc;
+    }
+  }
+}
+
+__host__ __device__ constexpr bool gen_has_butterfly(unsigned p) {
+  return p == 2 || p == 3 || p == 4 || p == 5 || p == 7 || p == 8 || p == 11 || p == 13;
+}
+template <bool SRC_SMEM, bool DST_SMEM>
+__device__ __forceinline__ void gen_pass(unsigned p, const float2* src, float2* dst, const float2* __restrict__ tw, unsigned n, unsigned ns,
+                                         unsigned slots, bool conj_in, bool conj_out, bool do_scale, float scale) {
+  switch (p) {
+#define AE_P(PP) case PP: gen_butterfly_pass<PP, SRC_SMEM, DST_SMEM>(src, dst, tw, n, ns, slots, conj_in, conj_out, do_scale, scale); break;
+    AE_P(2) AE_P(3) AE_P(4) AE_P(5) AE_P(7) AE_P(8) AE_P(11) AE_P(13)
+#undef AE_P
+    default: gen_output_pass<SRC_SMEM, DST_SMEM>(src, dst, tw, n, p, ns, slots, conj_in, conj_out, do_scale, scale); break;
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) fft_generic_smem_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                               const float2* __restrict__ tw, unsigned n, size_t frames, unsigned slots,
                                                                const __grid_constant__ GenRadices rad, int inverse, int do_scale,
                                                                float scale) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* buf0 = reinterpret_cast<float2*>(smem_raw);
-  float2* buf1 = buf0 + n;
-  for (size_t frame = blockIdx.x; frame < frames; frame += gridDim.x) {
-    for (unsigned i = threadIdx.x; i < n; i += 256) buf0[i] = ld_stream(in + frame * n + i);
-    __syncthreads();
+  float2* buf1 = buf0 + gen_pad(slots * n) + 1;
+  for (size_t frame0 = (size_t)blockIdx.x * slots; frame0 < frames; frame0 += (size_t)gridDim.x * slots) {
+    const unsigned here = frames - frame0 < slots ? (unsigned)(frames - frame0) : slots;
+    const float2* gin = in + frame0 * n;
+    float2* gout = out + frame0 * n;
     float2* cur = buf0;
     float2* nxt = buf1;
     unsigned ns = 1;
-    for (int pi = 0; pi < rad.count; ++pi) {
-      const unsigned p = rad.r[pi], m = n / p, tws = n / (ns * p), wp = n / p;
-      const bool last = (pi == rad.count - 1);
-      for (unsigned o = threadIdx.x; o < n; o += 256) {
-        const unsigned q = o / m, j = o - q * m, k = j % ns;
-        float2 acc = make_float2(0.0f, 0.0f);
-        // exponent of W_n for term r: r*k*tws (< n) + ((r*q) mod p)*wp (< n), both advanced incrementally
-        const unsigned step1 = k * tws;
-        unsigned e1 = 0, rq = 0;
-        for (unsigned r = 0; r < p; ++r) {
-          unsigned e = e1 + rq * wp;
-          if (e >= n) e -= n;
-          float2 w = __ldg(tw + e);
-          if (inverse) w.y = -w.y;
-          cx_fma(acc, cur[j + r * m], w);
-          e1 += step1;
-          rq += q;
-          if (rq >= p) rq -= p;
-        }
-        const unsigned dst = (j - k) * p + k + q * ns;
-        if (last) {
-          if (do_scale) acc = cx_scale_exact(acc, scale);
-          st_stream(out + frame * n + dst, acc);
-        } else {
-          nxt[dst] = acc;
-        }
-      }
+    // a first factor without a register butterfly reads every input from many threads: stage the frames
+    // in shared memory first (also keeps a single-pass in-place transform free of read/write races)
+    const bool staged = !gen_has_butterfly(rad.r[0]);
+    if (staged) {
+      for (unsigned i = threadIdx.x; i < here * n; i += blockDim.x) nxt[gen_pad(i)] = ld_stream(gin + i);
       __syncthreads();
-      float2* t = cur; cur = nxt; nxt = t;
+    }
+    for (int pi = 0; pi < rad.count; ++pi) {
+      const unsigned p = rad.r[pi];
+      const bool first = pi == 0, last = pi == rad.count - 1;
+      if (first && staged) {
+        if (last) gen_pass<true, false>(p, nxt, gout, tw, n, ns, here, inverse, inverse, do_scale, scale);
+        else gen_pass<true, true>(p, nxt, cur, tw, n, ns, here, inverse, false, false, scale);
+      }
+      else if (first && last) gen_pass<false, false>(p, gin, gout, tw, n, ns, here, inverse, inverse, do_scale, scale);
+      else if (first) gen_pass<false, true>(p, gin, cur, tw, n, ns, here, inverse, false, false, scale);
+      else if (last) gen_pass<true, false>(p, cur, gout, tw, n, ns, here, false, inverse, do_scale, scale);
+      else gen_pass<true, true>(p, cur, nxt, tw, n, ns, here, false, false, false, scale);
+      __syncthreads();
+      if (!first) { float2* t = cur; cur = nxt; nxt = t; }
       ns *= p;
     }
   }
+}
+
+static unsigned gen_slots(size_t n) {
+  size_t s = 2048 / n;
+  return (unsigned)(s < 1 ? 1 : (s > 64 ? 64 : s));
 }
 
 void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n, size_t frames, const float2* tw,
                         const uint32_t* radices, int n_radices, bool inverse, bool do_scale, float scale, cudaStream_t st) {
   if (frames == 0 || n == 0) return;
   if (n <= (size_t)kGenSmemMaxN && n_radices >= 1 && n_radices <= kGenMaxRadices) {
+    // odd radices first (their stride-P stores are conflict-free), then the powers of two merged into 8s
     GenRadices rad;
-    rad.count = n_radices;
-    for (int i = 0; i < n_radices; ++i) rad.r[i] = radices[i];
-    const size_t smem = 2 * n * sizeof(float2);
+    rad.count = 0;
+    unsigned twos = 0;
+    for (int i = 0; i < n_radices; ++i) {
+      if (radices[i] == 2) twos += 1;
+      else if (radices[i] == 4) twos += 2;
+      else if (radices[i] == 8) twos += 3;
+      else rad.r[rad.count++] = radices[i];
+    }
+    for (; twos >= 3 && rad.count < kGenMaxRadices; twos -= 3) rad.r[rad.count++] = 8;
+    if (twos == 2) rad.r[rad.count++] = 4;
+    if (twos == 1) rad.r[rad.count++] = 2;
+    const unsigned slots = gen_slots(n);
+    const size_t smem = 2 * ((size_t)slots * n + (slots * n) / 32 + 2) * sizeof(float2);
     if (smem > 48 * 1024) cudaFuncSetAttribute(fft_generic_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 1, dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_generic_smem_kernel, 256, smem);
     const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
-    fft_generic_smem_kernel<<<(unsigned)(frames < resident ? frames : resident), 256, smem, st>>>(in, out, tw, (unsigned)n, frames, rad, inverse,
-                                                                                                 do_scale, scale);
+    const size_t want = (frames + slots - 1) / slots;
+    fft_generic_smem_kernel<<<(unsigned)(want < resident ? want : resident), 256, smem, st>>>(in, out, tw, (unsigned)n, frames, slots, rad,
+                                                                                          inverse, do_scale, scale);
     return;
   }
   // scratch holds 2*n*frames cf32: ping-pong halves; the last pass writes `out`

@@ -167,3 +167,29 @@ def test_large_power_of_two_four_step(ae, n):
         assert same_bits(din.to_numpy(), x)
         (f.ibwd if bwd else f.ifwd)(din, sc, howmany=frames)      # in place
         assert same_bits(din.to_numpy(), got)
+
+
+@pytest.mark.parametrize("n", [6, 7, 11, 13, 14, 17, 34, 49, 77, 85, 91, 143, 169, 210, 289, 1001, 1536, 4199, 6000, 6144])
+def test_mixed_radix_lengths_with_ragged_frame_groups(ae, n):
+    """Any-length path: register butterflies for 2/3/4/5/7/8/11/13, per-output fallback for other primes
+    (17, 19), several frames per CTA — frame counts that do not fill the last CTA's slots, in place and
+    out of place, both directions."""
+    frames = 45 if n <= 1100 else 5
+    x = rnd(n * frames, n)
+    f = ae.Cfft.with_len(n)
+    for bwd in (False, True):
+        want = o.cfft(x, n, bwd=bwd, scale_kind=o.SCALE_SN, scale_x=1.0, compat=ae.COMPAT_REFERENCE)
+        din = ae.DeviceVec.from_numpy(x)
+        dout = ae.DeviceVec.zeros(x.size)
+        (f.bwd if bwd else f.fwd)(din, dout, ae.Scale.SN, howmany=frames)
+        got = dout.to_numpy()
+        assert evm_db(got, want) <= EVM_LIMIT_DB
+        for fr in range(frames):     # per frame, so one bad frame cannot hide in the average
+            assert evm_db(got[fr * n:(fr + 1) * n], want[fr * n:(fr + 1) * n]) <= EVM_LIMIT_DB
+        (f.ibwd if bwd else f.ifwd)(din, ae.Scale.SN, howmany=frames)
+        assert same_bits(din.to_numpy(), got)
+    # round trip: bwd(fwd(x)) with Scale::SN both ways returns x (src/fft.rs:93-117 doctest pattern)
+    d = ae.DeviceVec.from_numpy(x)
+    f.ifwd(d, ae.Scale.SN, howmany=frames)
+    f.ibwd(d, ae.Scale.SN, howmany=frames)
+    assert evm_db(d.to_numpy(), x) <= EVM_LIMIT_DB
