@@ -318,7 +318,14 @@ __global__ void __launch_bounds__(256) fft_generic_pass_kernel(const float2* __r
 // transform is conj -> forward -> conj, applied at the first load and the last store.
 constexpr int kGenSmemMaxN = 6144;
 constexpr int kGenMaxRadices = 16;
-struct GenRadices { unsigned r[kGenMaxRadices]; int count; };
+// per pass: radix p, m = n/p butterflies, ns = product of the earlier radices, and 2^32/d "magic"
+// reciprocals so the index arithmetic needs no integer division (exact while x*d < 2^32)
+struct GenPass { unsigned p, m, ns, tws, mg_m, mg_ns; };
+struct GenRadices { GenPass pass[kGenMaxRadices]; unsigned mg_n; int count; };
+// floor(x / d) with magic = ceil(2^32 / d) (0 encodes d == 1).  mul.hi through the intrinsic: the same
+// arithmetic written as a 64-bit product and shift was folded by nvcc 12.9 into x*hi32(magic*-d)+x,
+// which is wrong (N = 12 crashed with an illegal address).
+__device__ __forceinline__ unsigned gen_div(unsigned x, unsigned magic) { return magic ? __umulhi(x, magic) : x; }
 
 __device__ __forceinline__ unsigned gen_pad(unsigned i) { return i + (i >> 5); }
 
@@ -354,9 +361,9 @@ __device__ __forceinline__ void odd_dft(float2 (&v)[P], const float2 (&root)[(P 
 }
 
 template <int P, bool SRC_SMEM, bool DST_SMEM>
-__device__ __forceinline__ void gen_butterfly_pass(const float2* src, float2* dst, const float2* __restrict__ tw, unsigned n, unsigned ns,
+__device__ __forceinline__ void gen_butterfly_pass(const float2* src, float2* dst, const float2* __restrict__ tw, unsigned n, const GenPass& gp,
                                                    unsigned slots, bool conj_in, bool conj_out, bool do_scale, float scale) {
-  const unsigned m = n / P, tws = n / (ns * P);
+  const unsigned m = gp.m, tws = gp.tws, ns = gp.ns;
   constexpr int H = (P - 1) / 2;
   float2 root[H + 1];
   if constexpr (P & 1) {
@@ -364,7 +371,7 @@ __device__ __forceinline__ void gen_butterfly_pass(const float2* src, float2* ds
     for (int r = 1; r <= H; ++r) root[r] = __ldg(tw + r * m);
   }
   for (unsigned item = threadIdx.x; item < slots * m; item += blockDim.x) {
-    const unsigned s = item / m, j = item - s * m, k = j % ns, sb = s * n;
+        const unsigned s = gen_div(item, gp.mg_m), j = item - s * m, k = j - gen_div(j, gp.mg_ns) * ns, sb = s * n;
     float2 v[P];
 #pragma unroll
     for (int r = 0; r < P; ++r) {
@@ -396,11 +403,11 @@ __device__ __forceinline__ void gen_butterfly_pass(const float2* src, float2* ds
 
 // any radix p: one output per thread, p terms (exponent of W_n for term r: r*k*tws + ((r*q) mod p)*n/p)
 template <bool SRC_SMEM, bool DST_SMEM>
-__device__ __forceinline__ void gen_output_pass(const float2* src, float2* dst, const float2* __restrict__ tw, unsigned n, unsigned p,
-                                                unsigned ns, unsigned slots, bool conj_in, bool conj_out, bool do_scale, float scale) {
-  const unsigned m = n / p, tws = n / (ns * p), wp = n / p;
+__device__ __forceinline__ void gen_output_pass(const float2* src, float2* dst, const float2* __restrict__ tw, unsigned n, const GenPass& gp,
+                                                unsigned mg_n, unsigned slots, bool conj_in, bool conj_out, bool do_scale, float scale) {
+  const unsigned p = gp.p, m = gp.m, tws = gp.tws, wp = gp.m, ns = gp.ns;
   for (unsigned o = threadIdx.x; o < slots * n; o += blockDim.x) {
-    const unsigned s = o / n, oo = o - s * n, q = oo / m, j = oo - q * m, k = j % ns, sb = s * n;
+    const unsigned s = gen_div(o, mg_n), oo = o - s * n, q = gen_div(oo, gp.mg_m), j = oo - q * m, k = j - gen_div(j, gp.mg_ns) * ns, sb = s * n;
     float2 acc = make_float2(0.0f, 0.0f);
     const unsigned step1 = k * tws;
     unsigned e1 = 0, rq = 0;
@@ -431,13 +438,13 @@ __host__ __device__ constexpr bool gen_has_butterfly(unsigned p) {
   return p == 2 || p == 3 || p == 4 || p == 5 || p == 7 || p == 8 || p == 11 || p == 13;
 }
 template <bool SRC_SMEM, bool DST_SMEM>
-__device__ __forceinline__ void gen_pass(unsigned p, const float2* src, float2* dst, const float2* __restrict__ tw, unsigned n, unsigned ns,
-                                         unsigned slots, bool conj_in, bool conj_out, bool do_scale, float scale) {
-  switch (p) {
-#define AE_P(PP) case PP: gen_butterfly_pass<PP, SRC_SMEM, DST_SMEM>(src, dst, tw, n, ns, slots, conj_in, conj_out, do_scale, scale); break;
+__device__ __forceinline__ void gen_pass(const GenPass& gp, unsigned mg_n, const float2* src, float2* dst, const float2* __restrict__ tw,
+                                         unsigned n, unsigned slots, bool conj_in, bool conj_out, bool do_scale, float scale) {
+  switch (gp.p) {
+#define AE_P(PP) case PP: gen_butterfly_pass<PP, SRC_SMEM, DST_SMEM>(src, dst, tw, n, gp, slots, conj_in, conj_out, do_scale, scale); break;
     AE_P(2) AE_P(3) AE_P(4) AE_P(5) AE_P(7) AE_P(8) AE_P(11) AE_P(13)
 #undef AE_P
-    default: gen_output_pass<SRC_SMEM, DST_SMEM>(src, dst, tw, n, p, ns, slots, conj_in, conj_out, do_scale, scale); break;
+    default: gen_output_pass<SRC_SMEM, DST_SMEM>(src, dst, tw, n, gp, mg_n, slots, conj_in, conj_out, do_scale, scale); break;
   }
 }
 
@@ -448,40 +455,42 @@ __global__ void __launch_bounds__(256, 3) fft_generic_smem_kernel(const float2* 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* buf0 = reinterpret_cast<float2*>(smem_raw);
   float2* buf1 = buf0 + gen_pad(slots * n) + 1;
+  // the per-pass plan is read with a run-time index: keep it in shared memory
+  __shared__ GenPass plan[kGenMaxRadices];
+  if (threadIdx.x < rad.count) plan[threadIdx.x] = rad.pass[threadIdx.x];
+  __syncthreads();
   for (size_t frame0 = (size_t)blockIdx.x * slots; frame0 < frames; frame0 += (size_t)gridDim.x * slots) {
     const unsigned here = frames - frame0 < slots ? (unsigned)(frames - frame0) : slots;
     const float2* gin = in + frame0 * n;
     float2* gout = out + frame0 * n;
     float2* cur = buf0;
     float2* nxt = buf1;
-    unsigned ns = 1;
     // a first factor without a register butterfly reads every input from many threads: stage the frames
     // in shared memory first (also keeps a single-pass in-place transform free of read/write races)
-    const bool staged = !gen_has_butterfly(rad.r[0]);
+    const bool staged = !gen_has_butterfly(plan[0].p);
     if (staged) {
       for (unsigned i = threadIdx.x; i < here * n; i += blockDim.x) nxt[gen_pad(i)] = ld_stream(gin + i);
       __syncthreads();
     }
     for (int pi = 0; pi < rad.count; ++pi) {
-      const unsigned p = rad.r[pi];
+      const GenPass gp = plan[pi];
       const bool first = pi == 0, last = pi == rad.count - 1;
       if (first && staged) {
-        if (last) gen_pass<true, false>(p, nxt, gout, tw, n, ns, here, inverse, inverse, do_scale, scale);
-        else gen_pass<true, true>(p, nxt, cur, tw, n, ns, here, inverse, false, false, scale);
+        if (last) gen_pass<true, false>(gp, rad.mg_n, nxt, gout, tw, n, here, inverse, inverse, do_scale, scale);
+        else gen_pass<true, true>(gp, rad.mg_n, nxt, cur, tw, n, here, inverse, false, false, scale);
       }
-      else if (first && last) gen_pass<false, false>(p, gin, gout, tw, n, ns, here, inverse, inverse, do_scale, scale);
-      else if (first) gen_pass<false, true>(p, gin, cur, tw, n, ns, here, inverse, false, false, scale);
-      else if (last) gen_pass<true, false>(p, cur, gout, tw, n, ns, here, false, inverse, do_scale, scale);
-      else gen_pass<true, true>(p, cur, nxt, tw, n, ns, here, false, false, false, scale);
+      else if (first && last) gen_pass<false, false>(gp, rad.mg_n, gin, gout, tw, n, here, inverse, inverse, do_scale, scale);
+      else if (first) gen_pass<false, true>(gp, rad.mg_n, gin, cur, tw, n, here, inverse, false, false, scale);
+      else if (last) gen_pass<true, false>(gp, rad.mg_n, cur, gout, tw, n, here, false, inverse, do_scale, scale);
+      else gen_pass<true, true>(gp, rad.mg_n, cur, nxt, tw, n, here, false, false, false, scale);
       __syncthreads();
       if (!first) { float2* t = cur; cur = nxt; nxt = t; }
-      ns *= p;
     }
   }
 }
 
 static unsigned gen_slots(size_t n) {
-  size_t s = 2048 / n;
+  size_t s = 4096 / n;
   return (unsigned)(s < 1 ? 1 : (s > 64 ? 64 : s));
 }
 
@@ -490,18 +499,33 @@ void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n
   if (frames == 0 || n == 0) return;
   if (n <= (size_t)kGenSmemMaxN && n_radices >= 1 && n_radices <= kGenMaxRadices) {
     // odd radices first (their stride-P stores are conflict-free), then the powers of two merged into 8s
-    GenRadices rad;
-    rad.count = 0;
+    unsigned order[kGenMaxRadices];
+    int cnt = 0;
     unsigned twos = 0;
     for (int i = 0; i < n_radices; ++i) {
       if (radices[i] == 2) twos += 1;
       else if (radices[i] == 4) twos += 2;
       else if (radices[i] == 8) twos += 3;
-      else rad.r[rad.count++] = radices[i];
+      else order[cnt++] = radices[i];
     }
-    for (; twos >= 3 && rad.count < kGenMaxRadices; twos -= 3) rad.r[rad.count++] = 8;
-    if (twos == 2) rad.r[rad.count++] = 4;
-    if (twos == 1) rad.r[rad.count++] = 2;
+    for (; twos >= 3 && cnt < kGenMaxRadices; twos -= 3) order[cnt++] = 8;
+    if (twos == 2) order[cnt++] = 4;
+    if (twos == 1) order[cnt++] = 2;
+    auto magic = [](unsigned d) { return d <= 1 ? 0u : (unsigned)((0x100000000ull + d - 1) / d); };
+    GenRadices rad;
+    rad.count = cnt;
+    rad.mg_n = magic((unsigned)n);
+    unsigned ns = 1;
+    for (int i = 0; i < cnt; ++i) {
+      GenPass& gp = rad.pass[i];
+      gp.p = order[i];
+      gp.m = (unsigned)n / gp.p;
+      gp.ns = ns;
+      gp.tws = (unsigned)n / (ns * gp.p);
+      gp.mg_m = magic(gp.m);
+      gp.mg_ns = magic(ns);
+      ns *= gp.p;
+    }
     const unsigned slots = gen_slots(n);
     const size_t smem = 2 * ((size_t)slots * n + (slots * n) / 32 + 2) * sizeof(float2);
     if (smem > 48 * 1024) cudaFuncSetAttribute(fft_generic_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -297,6 +297,13 @@ def extras(torch, ae, d_in, frames, hbm_peak, steps=5, warmup=3):
     sigv = ae.DeviceVec.zeros(FFT_LEN)
     t = timed(torch, lambda: ae.spectral.correlate(d_in, sigv, fft, ae.Scale.SN, howmany=frames), steps, warmup) / steps
     rec("correlator1024", 16.0 * n, t, n, "samples")
+    # any-length path (mixed-radix shared-memory kernel): N = 100 is the reference's own test length
+    for nn in (100, 1000):
+        fr = (1 << 27) // nn
+        fo = ae.Cfft.with_len(nn)
+        vo = d_in.view(0, fr * nn)
+        t = timed(torch, lambda: fo.ifwd(vo, ae.Scale.SN, howmany=fr), steps, warmup) / steps
+        rec("fft%d_fwd_SN" % nn, 16.0 * fr * nn, t, fr * nn, "samples")
     t = timed(torch, lambda: d_in.vec_stats(), steps, warmup) / steps
     rec("vecstats_cf32", 8.0 * n, t, n, "samples")
     # config 5: OFDM-like chain, 2048-pt, 2^18 frames, counters only
