@@ -22,7 +22,7 @@ st = DeviceStats()
 qpsk = ae.modulation.qpsk()
 g = ae.noise.new(0.01, 815)
 fft = ae.Cfft.with_len(1024)
-for rep in range(2):
+for rep in range(1):
     dx.vec_mul(dy).vec_conj().vec_mirror().flush()
     dx.vec_scale(0.5).vec_add(dy).flush()
     ds = ae.DeviceVec.zeros(n // 4)
@@ -46,8 +46,19 @@ for rep in range(2):
     del bits, sym, fv, out
     fft.ifwd(dx, ae.Scale.SN, howmany=n // 1024)
     lv = ae.spectral.spectrogram(dx, fft, True)
-    ae.spectral.correlate(dx, ae.DeviceVec.zeros(1024), fft, ae.Scale.SN, howmany=n // 1024)
+    sig = ae.DeviceVec.from_torch(torch.view_as_complex(torch.randn(1024, 2, device="cuda")))
+    ae.spectral.correlate(dx, sig, fft, ae.Scale.SN, howmany=n // 1024)
+    lv.vec_stats()
     del lv
+    dx.vec_stats()
+    for nn in (100, 1000, 3000):                       # any-length mixed-radix kernel
+        fr = n // nn
+        ae.Cfft.with_len(nn).ifwd(dx.view(0, fr * nn), ae.Scale.SN, howmany=fr)
+    ae.Cfft.with_len(1 << 16).ifwd(dx, ae.Scale.SN, howmany=n >> 16)      # four-step
+    from aether_primitives_b200.chain import FftFirDemod
+    cb = ae.DeviceBits.with_capacity(2 * n)
+    FftFirDemod(1024, make_taps(64), ae.Scale.SN).run(dx, cb)              # headline chain
+    del cb
     ae.chain.ofdm_chain(2048, 1 << 14, 0, 0.05, 5, st)
     seq = ae.sequence.generate([1] + [0] * 30, [28, 31], 1 << 24)
     del seq
