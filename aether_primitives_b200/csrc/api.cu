@@ -600,6 +600,11 @@ struct ae_fft {
   float2 *tw1 = nullptr, *tw2 = nullptr;  // per-thread tables of the two factor lengths
   float2 *wlo = nullptr, *whi = nullptr;  // two-level W_len table (owned)
   std::vector<uint32_t> radices;
+  // Bluestein path (non-power-of-two lengths > 6144 or with a prime factor > 61)
+  bool blue = false;
+  unsigned blue_log2m = 0;
+  ae_fft* blue_child = nullptr;            // power-of-two plan of length M = 2^blue_log2m
+  float2 *blue_w = nullptr, *blue_b = nullptr;   // chirp w[n] (len entries), FFT_M of the wrapped conj chirp (M entries)
   float2* scratch;
   size_t scratch_elems;
   Alloc* tmp;       // tfwd/tbwd result buffer
@@ -631,6 +636,24 @@ ae_status fft_run(ae_fft* f, int dir, const float2* in, float2* out, int scale_k
     }
     launch_fft_big(in, out, f->scratch, f->len, howmany, f->tw1, f->tw2, f->wlo, f->whi, inverse, do_scale, s, c->stream);
     CKL(2 * ((howmany + 32767) / 32768));
+  } else if (f->blue) {
+    const size_t m = (size_t)1 << f->blue_log2m;
+    const size_t need = m * howmany;
+    if (f->scratch_elems < need) {
+      dev_free(c, f->scratch);
+      f->scratch = nullptr; f->scratch_elems = 0;
+      void* p;
+      TRY(dev_alloc(c, need * sizeof(float2), &p));
+      f->scratch = (float2*)p; f->scratch_elems = need;
+    }
+    launch_bluestein_pre(in, f->scratch, f->blue_w, f->len, f->blue_log2m, howmany, inverse, c->sm_count, c->stream);
+    CKL(1);
+    TRY(fft_run(f->blue_child, AE_FFT_FWD, f->scratch, f->scratch, AE_SCALE_NONE, 1.0f, howmany));
+    launch_bluestein_mul(f->scratch, f->blue_b, f->blue_log2m, howmany, c->sm_count, c->stream);
+    CKL(1);
+    TRY(fft_run(f->blue_child, AE_FFT_BWD, f->scratch, f->scratch, AE_SCALE_NONE, 1.0f, howmany));
+    launch_bluestein_post(f->scratch, out, f->blue_w, f->len, f->blue_log2m, howmany, inverse, do_scale, s, c->stream);
+    CKL((howmany + 32767) / 32768);
   } else {
     const size_t need = 2 * f->len * howmany;
     if (f->scratch_elems < need) {
@@ -711,6 +734,43 @@ ae_status ae_fft_create(size_t len, ae_fft** out) {
   }
   f->tmpview.c = c; f->tmpview.a = nullptr; f->tmpview.off = 0; f->tmpview.len = 0; f->tmpview.cap = 0;
   f->tmpview.plan_owned = true;
+  if (!f->pow2 && !f->big) {
+    uint32_t pmax = 1;
+    for (uint32_t r : f->radices) pmax = std::max(pmax, r);
+    if (len > 6144 || pmax > 61) {
+      // Bluestein: M = the power of two >= 2*len - 1; chirp exponents n^2 mod 2N are exact integers
+      unsigned lg = 1;
+      while (((size_t)1 << lg) < 2 * len - 1) ++lg;
+      const size_t m = (size_t)1 << lg;
+      ae_status st2 = ae_fft_create(m, &f->blue_child);
+      if (st2 == AE_OK) st2 = ae_fft_set_compat(f->blue_child, AE_COMPAT_CORRECTED);   // FWD = exp(-)
+      std::vector<float2> w(len), b(m, make_float2(0.0f, 0.0f));
+      for (size_t n = 0; n < len; ++n) {
+        const unsigned long long e = ((unsigned long long)n * n) % (2ull * len);
+        const double a = -M_PI * (double)e / (double)len;
+        w[n] = make_float2((float)std::cos(a), (float)std::sin(a));
+        const float2 cw = make_float2(w[n].x, -w[n].y);
+        b[n] = cw;
+        if (n) b[m - n] = cw;
+      }
+      void* p = nullptr;
+      if (st2 == AE_OK) st2 = dev_alloc(c, len * sizeof(float2), &p);
+      if (st2 == AE_OK) {
+        f->blue_w = (float2*)p;
+        cudaMemcpyAsync(f->blue_w, w.data(), len * sizeof(float2), cudaMemcpyHostToDevice, c->stream);
+        st2 = dev_alloc(c, m * sizeof(float2), &p);
+      }
+      if (st2 == AE_OK) {
+        f->blue_b = (float2*)p;
+        cudaMemcpyAsync(f->blue_b, b.data(), m * sizeof(float2), cudaMemcpyHostToDevice, c->stream);
+        st2 = fft_run(f->blue_child, AE_FFT_FWD, f->blue_b, f->blue_b, AE_SCALE_NONE, 1.0f, 1);
+      }
+      if (st2 == AE_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st2 = fail(AE_ECUDA, "Bluestein plan setup failed");
+      if (st2 != AE_OK) { ae_fft_destroy(f); return st2; }
+      f->blue = true;
+      f->blue_log2m = lg;
+    }
+  }
   *out = f;
   return AE_OK;
 }
@@ -720,6 +780,8 @@ ae_status ae_fft_destroy(ae_fft* f) {
   dev_free(f->c, f->scratch);
   dev_free(f->c, f->wlo);
   dev_free(f->c, f->whi);
+  dev_free(f->c, f->blue_w); dev_free(f->c, f->blue_b);
+  ae_fft_destroy(f->blue_child);
   if (f->tmp) { flush_vec(&f->tmpview); alloc_unref(f->c, f->tmp); }
   delete f;
   return AE_OK;

@@ -567,4 +567,69 @@ void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Bluestein (chirp-z) for lengths the mixed-radix kernels handle badly: non-power-of-two N > 6144 and
+// N with a large prime factor.  With w[n] = exp(-i pi n^2 / N):
+//     X[k] = w[k] * sum_n (x[n] w[n]) * conj(w[k-n])
+// i.e. one circular convolution of length M >= 2N-1 (a power of two), done with the power-of-two
+// kernels: a = pad(x.*w) -> FFT_M -> .* B -> inverse FFT_M -> .* w / M, where B = FFT_M(chirp) is
+// part of the plan.  The inverse transform is conj -> forward -> conj.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bluestein_pre_kernel(const float2* __restrict__ in, float2* __restrict__ a, const float2* __restrict__ w,
+                                                            unsigned n, unsigned log2m, size_t frames, int conj_in) {
+  const size_t total = frames << log2m;
+  const unsigned mask = (1u << log2m) - 1u;
+  for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256) {
+    const size_t f = idx >> log2m;
+    const unsigned j = (unsigned)idx & mask;
+    float2 v = make_float2(0.0f, 0.0f);
+    if (j < n) {
+      v = ld_stream(in + f * n + j);
+      if (conj_in) v.y = -v.y;
+      v = cx_mul(v, __ldg(w + j));
+    }
+    a[idx] = v;
+  }
+}
+__global__ void __launch_bounds__(256) bluestein_mul_kernel(float2* __restrict__ a, const float2* __restrict__ bspec, unsigned log2m, size_t total) {
+  const unsigned mask = (1u << log2m) - 1u;
+  for (size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (size_t)gridDim.x * 256)
+    a[idx] = cx_mul(a[idx], __ldg(bspec + ((unsigned)idx & mask)));
+}
+__global__ void __launch_bounds__(256) bluestein_post_kernel(const float2* __restrict__ c, float2* __restrict__ out, const float2* __restrict__ w,
+                                                             unsigned n, unsigned log2m, float inv_m, int conj_out, int do_scale, float scale) {
+  const size_t f = blockIdx.y;
+  const unsigned k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= n) return;
+  float2 y = cx_mul(c[(f << log2m) + k], __ldg(w + k));
+  y.x *= inv_m; y.y *= inv_m;
+  if (conj_out) y.y = -y.y;
+  if (do_scale) y = cx_scale_exact(y, scale);
+  st_stream(out + f * n + k, y);
+}
+
+void launch_bluestein_pre(const float2* in, float2* a, const float2* w, size_t n, unsigned log2m, size_t frames, bool conj_in, int sm_count,
+                          cudaStream_t st) {
+  const size_t total = frames << log2m;
+  size_t g = (total + 255) / 256;
+  const size_t cap = (size_t)sm_count * 16;
+  bluestein_pre_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(in, a, w, (unsigned)n, log2m, frames, conj_in);
+}
+void launch_bluestein_mul(float2* a, const float2* bspec, unsigned log2m, size_t frames, int sm_count, cudaStream_t st) {
+  const size_t total = frames << log2m;
+  size_t g = (total + 255) / 256;
+  const size_t cap = (size_t)sm_count * 16;
+  bluestein_mul_kernel<<<(unsigned)(g < cap ? g : cap), 256, 0, st>>>(a, bspec, log2m, total);
+}
+void launch_bluestein_post(const float2* c, float2* out, const float2* w, size_t n, unsigned log2m, size_t frames, bool conj_out,
+                           bool do_scale, float scale, cudaStream_t st) {
+  constexpr size_t kMaxY = 32768;
+  const float inv_m = 1.0f / (float)(1ull << log2m);
+  for (size_t f0 = 0; f0 < frames; f0 += kMaxY) {
+    const size_t fc = frames - f0 < kMaxY ? frames - f0 : kMaxY;
+    const dim3 grid((unsigned)((n + 255) / 256), (unsigned)fc);
+    bluestein_post_kernel<<<grid, 256, 0, st>>>(c + (f0 << log2m), out + f0 * n, w, (unsigned)n, log2m, inv_m, conj_out, do_scale, scale);
+  }
+}
+
 }  // namespace ae

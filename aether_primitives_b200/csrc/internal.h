@@ -69,6 +69,12 @@ void fft_big_split(size_t n, size_t* n1, size_t* n2);
 void launch_fft_big(const float2* in, float2* out, float2* scratch, size_t n, size_t frames, const float2* tw1, const float2* tw2,
                     const float2* wlo, const float2* whi, bool inverse, bool do_scale, float scale, cudaStream_t st);
 // any length: one global-memory Stockham pass per prime-power factor; needs 2 scratch buffers
+// Bluestein helpers (any length through the power-of-two kernels); log2m = log2 of the padded length
+void launch_bluestein_pre(const float2* in, float2* a, const float2* w, size_t n, unsigned log2m, size_t frames, bool conj_in, int sm_count,
+                          cudaStream_t st);
+void launch_bluestein_mul(float2* a, const float2* bspec, unsigned log2m, size_t frames, int sm_count, cudaStream_t st);
+void launch_bluestein_post(const float2* c, float2* out, const float2* w, size_t n, unsigned log2m, size_t frames, bool conj_out,
+                           bool do_scale, float scale, cudaStream_t st);
 void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n, size_t frames, const float2* tw,
                         const uint32_t* radices, int n_radices, bool inverse, bool do_scale, float scale,
                         cudaStream_t st);

@@ -193,3 +193,29 @@ def test_mixed_radix_lengths_with_ragged_frame_groups(ae, n):
     f.ifwd(d, ae.Scale.SN, howmany=frames)
     f.ibwd(d, ae.Scale.SN, howmany=frames)
     assert evm_db(d.to_numpy(), x) <= EVM_LIMIT_DB
+
+
+@pytest.mark.parametrize("n", [67, 134, 1009, 4099, 6145, 7919, 8198, 10000, 12288, 12289, 20000, 3 * 16384 + 1])
+def test_bluestein_lengths(ae, n):
+    """Non-power-of-two lengths above 6144 and lengths with a prime factor > 61 run as a chirp-z
+    convolution over the power-of-two kernels: same contract as every other length (all scales,
+    both directions, in place and out of place, EVM <= -80 dB vs the oracle per frame)."""
+    frames = 3
+    x = rnd(n * frames, n)
+    f = ae.Cfft.with_len(n)
+    for bwd in (False, True):
+        for sc, ok, ox in ((ae.Scale.None_, o.SCALE_NONE, 1.0), (ae.Scale.SN, o.SCALE_SN, 1.0)):
+            want = o.cfft(x, n, bwd=bwd, scale_kind=ok, scale_x=ox, compat=ae.COMPAT_REFERENCE)
+            din = ae.DeviceVec.from_numpy(x)
+            dout = ae.DeviceVec.zeros(x.size)
+            (f.bwd if bwd else f.fwd)(din, dout, sc, howmany=frames)
+            got = dout.to_numpy()
+            for fr in range(frames):
+                assert evm_db(got[fr * n:(fr + 1) * n], want[fr * n:(fr + 1) * n]) <= EVM_LIMIT_DB
+            assert same_bits(din.to_numpy(), x)
+            (f.ibwd if bwd else f.ifwd)(din, sc, howmany=frames)
+            assert same_bits(din.to_numpy(), got)
+    d = ae.DeviceVec.from_numpy(x)
+    f.ifwd(d, ae.Scale.SN, howmany=frames)
+    f.ibwd(d, ae.Scale.SN, howmany=frames)
+    assert evm_db(d.to_numpy(), x) <= EVM_LIMIT_DB
