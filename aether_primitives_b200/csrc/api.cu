@@ -737,7 +737,7 @@ ae_status ae_fft_create(size_t len, ae_fft** out) {
   if (!f->pow2 && !f->big) {
     uint32_t pmax = 1;
     for (uint32_t r : f->radices) pmax = std::max(pmax, r);
-    if (len > 6144 || pmax > 61) {
+    if ((len & (len - 1)) != 0 && (len > 6144 || pmax > 61)) {   // (a power of two beyond the four-step range keeps the per-factor path)
       // Bluestein: M = the power of two >= 2*len - 1; chirp exponents n^2 mod 2N are exact integers
       unsigned lg = 1;
       while (((size_t)1 << lg) < 2 * len - 1) ++lg;
