@@ -873,6 +873,10 @@ ae_status ae_fir_create(const ae_cf32* taps_host, size_t ntaps, int mode, ae_fir
   TRY(get_ctx(&c));
   size_t nfft = 1024;
   while (nfft < 4 * ntaps) nfft <<= 1;
+  if (const char* e = getenv("AE_FIR_NFFT")) {   // developer override of the overlap-save block length
+    const size_t v = (size_t)atoll(e);
+    if (v >= 2 * ntaps) nfft = v;
+  }
   const bool os_ok = fir_os_supported(nfft) && ntaps <= nfft / 2;
   const bool direct_ok = ntaps <= 4096;
   if (mode == AE_FIR_AUTO) mode = (ntaps <= 24 || !os_ok) ? AE_FIR_DIRECT : AE_FIR_OVERLAP_SAVE;
