@@ -289,7 +289,7 @@ struct OfdmLaunch {
 
 template <int N, bool FWD_INV>  // FWD_INV: exponent sign of Cfft::fwd is + (compat=reference)
 __global__ void __launch_bounds__(OfdmLaunch<N>::THREADS, OfdmLaunch<N>::THREADS <= 128 ? 4 : 2)
-ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int twice, uint64_t seed, const float2* __restrict__ tw,
+ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int twice, const __grid_constant__ PhiloxKeys keys, const float2* __restrict__ tw,
                   const uint32_t* __restrict__ zcol, int compat, uint8_t* __restrict__ tx_bits, uint8_t* __restrict__ rx_bits,
                   ae_stats* stats) {
   using C = FftCfg<N>;
@@ -349,7 +349,7 @@ ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int tw
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
       float2 z0, z1;
-      awgn_unit_pair(seed, frame_id, (uint64_t)(t + m * C::T), z0, z1);
+      awgn_unit_pair(keys, frame_id, (uint64_t)(t + m * C::T), z0, z1);
       z0 = cx_scale_exact(z0, noise_scale); z1 = cx_scale_exact(z1, noise_scale);
       if (twice) { z0 = cx_scale_exact(z0, noise_scale); z1 = cx_scale_exact(z1, noise_scale); }
       v[m] = cx_add_exact(v[m], z0);
@@ -447,7 +447,7 @@ static void launch_ofdm_n(size_t frames, uint64_t first_frame, float noise_scale
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, smem);
     const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
     const unsigned grid = (unsigned)(want < resident ? want : resident);
-    kern<<<grid, LC::THREADS, smem, st>>>(frames, first_frame, noise_scale, twice, seed, tw, zj, compat, tx_bits, rx_bits, stats);
+    kern<<<grid, LC::THREADS, smem, st>>>(frames, first_frame, noise_scale, twice, make_philox_keys(seed), tw, zj, compat, tx_bits, rx_bits, stats);
   };
   if (compat == AE_COMPAT_REFERENCE) launch(ofdm_chain_kernel<N, true>);
   else launch(ofdm_chain_kernel<N, false>);

@@ -149,29 +149,55 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// The ten round keys of a Philox4x32-10 stream depend only on the seed: the host expands them once
+// (make_philox_keys) and kernels take them as a __grid_constant__ parameter, so the XORs read them
+// straight from the constant bank instead of every thread re-deriving 20 key words per block.
+struct PhiloxKeys { uint32_t k0[10], k1[10]; };
+__host__ __device__ inline PhiloxKeys make_philox_keys(uint64_t seed) {
+  PhiloxKeys k;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) { k.k0[r] = a; k.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+  return k;
+}
+__device__ __forceinline__ void philox4x32_10_keys(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& k, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.k0[r];
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k.k1[r];
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float sfu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sfu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // Box-Muller on two 32-bit words -> two independent N(0,1) f32.
 // AWGN is validated statistically (tier T2), so the transcendental part uses the SFU:
-//   log : MUFU.LG2-based __logf, except within 2^-6 of 1 where its absolute error would dominate the
-//         tiny result: there log(1 - t) = -t(1 + t/2 + t^2/3 + t^3/4) (t = 1 - u1 is exact);
+//   log : MUFU.LG2 (u1 >= 2^-33 is never subnormal), except within 2^-6 of 1 where its absolute error
+//         would dominate the tiny result: there log(1 - t) = -t(1 + t/2 + t^2/3 + t^3/4) (t = 1 - u1 is exact);
+//   sqrt: MUFU-based sqrt.approx (<= 2 ulp; exact 0 for u1 == 1);
 //   trig: MUFU-based __sincosf on theta - pi in (-pi, pi], negated (cos/sin(theta) = -cos/sin(theta - pi)).
 // |dz| stays below ~3e-6 sigma of the full-precision evaluation (tests compare with the oracle's).
 __device__ __forceinline__ float2 gauss_pair(uint32_t a, uint32_t b) {
   const float u1 = __fmaf_rn(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
   const float u2 = __fmaf_rn(__uint2float_rn(b), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
   const float t = 1.0f - u1;
-  const float near1 = -t * fmaf(t, fmaf(t, fmaf(t, 0.25f, 0.33333334f), 0.5f), 1.0f);
-  const float l = t < 0.015625f ? near1 : __logf(u1);
-  const float r = sqrtf(-2.0f * l);
+  const float near1 = t * fmaf(t, fmaf(t, fmaf(t, 0.5f, 0.66666669f), 1.0f), 2.0f);   // -2 log(1 - t)
+  const float m2l = t < 0.015625f ? near1 : -1.3862943611198906f * sfu_lg2(u1);          // -2 ln u1 = -2 ln2 lg2 u1
+  const float r = sfu_sqrt(m2l);
   float s, c;
   __sincosf(fmaf(u2, 6.28318530717958647692f, -3.14159265358979323846f), &s, &c);
   return make_float2(-r * c, -r * s);
 }
 
-// unit-variance complex normals for the sample PAIR (2*pair, 2*pair+1) of a stream
-__device__ __forceinline__ void awgn_unit_pair(uint64_t seed, uint64_t stream, uint64_t pair, float2& z0, float2& z1) {
+// noise pair for Philox block `pair` of stream (keys, stream): z0 = samples 2*pair, z1 = 2*pair+1
+__device__ __forceinline__ void awgn_unit_pair(const PhiloxKeys& keys, uint64_t stream, uint64_t pair, float2& z0, float2& z1) {
   uint32_t o[4];
-  philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)stream, (uint32_t)(stream >> 32),
-                (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  philox4x32_10_keys((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)stream, (uint32_t)(stream >> 32), keys, o);
   z0 = gauss_pair(o[0], o[1]);
   z1 = gauss_pair(o[2], o[3]);
 }

@@ -328,14 +328,14 @@ void launch_demod(const ModTable& tab, const float2* sym, size_t n, uint8_t* bit
 // stream; results depend only on (seed, stream, global sample index), never on the grid shape.
 // =================================================================================================
 template <bool APPLY>
-__global__ void __launch_bounds__(256) awgn_kernel(float2* __restrict__ buf, size_t n, float scale, int twice, uint64_t seed,
-                                                   uint64_t stream, uint64_t offset, int vec_ok) {
+__global__ void __launch_bounds__(256) awgn_kernel(float2* __restrict__ buf, size_t n, float scale, int twice,
+                                                   const __grid_constant__ PhiloxKeys keys, uint64_t stream, uint64_t offset, int vec_ok) {
   const uint64_t p0 = offset >> 1;
   const uint64_t P = p0 + (uint64_t)blockIdx.x * 256 + threadIdx.x;
   const uint64_t g0 = 2 * P, g1 = g0 + 1;
   if (g0 >= offset + n) return;
   float2 z0, z1;
-  awgn_unit_pair(seed, stream, P, z0, z1);
+  awgn_unit_pair(keys, stream, P, z0, z1);
   // next(): (N(0,1) as f32) * scale (:41-42); apply(): ... .scale(sc) once more (:58)
   z0 = cx_scale_exact(z0, scale); z1 = cx_scale_exact(z1, scale);
   if (twice) { z0 = cx_scale_exact(z0, scale); z1 = cx_scale_exact(z1, scale); }
@@ -359,8 +359,9 @@ static void awgn_launch(bool apply, float2* buf, size_t n, float scale, int twic
   const uint64_t pairs = ((offset + n + 1) >> 1) - (offset >> 1);
   const int vec_ok = ((offset & 1) == 0) && ((uintptr_t)buf % 16) == 0;
   const unsigned g = cdiv(pairs, 256);
-  if (apply) awgn_kernel<true><<<g, 256, 0, st>>>(buf, n, scale, twice, seed, stream, offset, vec_ok);
-  else awgn_kernel<false><<<g, 256, 0, st>>>(buf, n, scale, twice, seed, stream, offset, vec_ok);
+  const PhiloxKeys keys = make_philox_keys(seed);
+  if (apply) awgn_kernel<true><<<g, 256, 0, st>>>(buf, n, scale, twice, keys, stream, offset, vec_ok);
+  else awgn_kernel<false><<<g, 256, 0, st>>>(buf, n, scale, twice, keys, stream, offset, vec_ok);
 }
 void launch_awgn_fill(float2* dst, size_t n, float scale, uint64_t seed, uint64_t stream, uint64_t offset, cudaStream_t st) {
   awgn_launch(false, dst, n, scale, 0, seed, stream, offset, st);
@@ -391,8 +392,8 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 // =================================================================================================
 template <int M>
 __global__ void __launch_bounds__(256) modem_kernel(const __grid_constant__ ModTable tabp, const uint8_t* __restrict__ bin, size_t nsym,
-                                                    uint8_t* __restrict__ bout, float scale, int twice, uint64_t seed, uint64_t stream,
-                                                    uint64_t offset, int compat, ae_stats* stats, int* errflag, int vec_ok) {
+                                                    uint8_t* __restrict__ bout, float scale, int twice, const __grid_constant__ PhiloxKeys keys,
+                                                    uint64_t stream, uint64_t offset, int compat, ae_stats* stats, int* errflag, int vec_ok) {
   constexpr int BPS = M == 2 ? 1 : 2;
   float2 tab[M];
 #pragma unroll
@@ -420,8 +421,8 @@ __global__ void __launch_bounds__(256) modem_kernel(const __grid_constant__ ModT
       }
     }
     float2 z[4];
-    awgn_unit_pair(seed, stream, p0 + q, z[0], z[1]);
-    awgn_unit_pair(seed, stream, p0 + q + 1, z[2], z[3]);
+    awgn_unit_pair(keys, stream, p0 + q, z[0], z[1]);
+    awgn_unit_pair(keys, stream, p0 + q + 1, z[2], z[3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long long l = l0 + i;
@@ -473,10 +474,11 @@ void launch_modem_fused(const ModTable& tab, const uint8_t* bits_in, size_t nbit
   unsigned g = cdiv(cdiv(npairs, 2), 256);
   const unsigned cap = (unsigned)sm_count * 16;
   if (g > cap) g = cap;
+  const PhiloxKeys keys = make_philox_keys(seed);
   if (tab.len == 2)
-    modem_kernel<2><<<g, 256, 0, st>>>(tab, bits_in, nsym, bits_out, scale, twice, seed, stream, offset, compat, stats, errflag, vec_ok);
+    modem_kernel<2><<<g, 256, 0, st>>>(tab, bits_in, nsym, bits_out, scale, twice, keys, stream, offset, compat, stats, errflag, vec_ok);
   else
-    modem_kernel<4><<<g, 256, 0, st>>>(tab, bits_in, nsym, bits_out, scale, twice, seed, stream, offset, compat, stats, errflag, vec_ok);
+    modem_kernel<4><<<g, 256, 0, st>>>(tab, bits_in, nsym, bits_out, scale, twice, keys, stream, offset, compat, stats, errflag, vec_ok);
 }
 
 // =================================================================================================
