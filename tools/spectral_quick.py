@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import aether_primitives_b200 as ae
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-frames = (1 << 29) // n
+frames = (1 << (int(sys.argv[2]) if len(sys.argv) > 2 else 29)) // n
 ae.init(0)
 ae.use_torch_stream()
 x = torch.view_as_complex(torch.randn(frames * n, 2, device="cuda"))
