@@ -235,7 +235,9 @@ def extras(torch, ae, d_in, frames, hbm_peak, steps=5, warmup=3):
     # config 4: fused mul.conj.mirror, downsample/4, interpolate x4 on 2^28 samples
     m = min(n, 1 << 28)
     a = d_in.view(0, m)
-    b = ae.DeviceVec.zeros(m)
+    # unit-modulus operand: eight repetitions of mul/conj/mirror leave the data N(0,1)-like for the
+    # kernels timed afterwards (a zero operand would hand the spectrogram all-zero frames)
+    b = ae.DeviceVec.from_torch(torch.full((m,), 0.6 + 0.8j, dtype=torch.complex64, device="cuda"))
     t = timed(torch, lambda: a.vec_mul(b).vec_conj().vec_mirror().flush(), steps, warmup) / steps
     rec("vecops_mul_conj_mirror_fused", 24.0 * m, t, m, "samples")
     ds = ae.DeviceVec.zeros(m // 4)
