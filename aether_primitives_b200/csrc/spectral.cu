@@ -24,12 +24,12 @@ struct SpecLaunch {
 };
 
 // level of one (already scaled) bin: c.norm() = hypot (num-complex), then 10*log10 when use_db
-// Fast path when |y|^2 neither overflows nor loses bits to underflow: sqrt(p) is within 1 ulp of hypot
+// Fast path when |y|^2 neither overflows nor loses bits to underflow: sqrt(p) is within 2 ulp of hypot
 // and 10 log10|y| = 5 log10(p) = 1.50515 log2(p) on the SFU (|error| < 2e-6 dB); otherwise the
 // library hypotf/log10f evaluate it (incl. |y| = 0 -> -inf, as DB::from(0.0) gives).
 __device__ __forceinline__ float level_of(float2 y, int use_db) {
   const float p = fmaf(y.x, y.x, y.y * y.y);
-  if (p > 1e-30f && p < 1e30f) return use_db ? 1.5051499783199058f * __log2f(p) : sqrtf(p);
+  if (p > 1e-30f && p < 1e30f) return use_db ? 1.5051499783199058f * sfu_lg2(p) : sfu_sqrt(p);   // MUFU, <= 2 ulp
   const float nrm = hypotf(y.x, y.y);
   return use_db ? 10.0f * log10f(nrm) : nrm;
 }
