@@ -137,7 +137,7 @@ ae_status ae_fft_exec_tmp(ae_fft* f, int dir, ae_vec* in, int scale_kind, float 
                           ae_vec** view);
 
 /* ---- fir (src/fir.rs:3-22 is a constructor-only stub; semantics defined in DESIGN.md) -- */
-enum { AE_FIR_AUTO = 0, AE_FIR_DIRECT = 1, AE_FIR_OVERLAP_SAVE = 2 };
+enum { AE_FIR_AUTO = 0, AE_FIR_DIRECT = 1, AE_FIR_OVERLAP_SAVE = 2 };   /* AUTO = overlap-save whenever a block length exists (faster at every tap count), else direct */
 ae_status ae_fir_create(const ae_cf32* taps_host, size_t ntaps, int mode, ae_fir** out); /* Fir::new :14 */
 ae_status ae_fir_destroy(ae_fir* f);
 size_t    ae_fir_ntaps(const ae_fir* f);

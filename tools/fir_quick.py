@@ -17,7 +17,10 @@ ae.use_torch_stream()
 x = torch.view_as_complex(torch.randn(n, 2, device="cuda"))
 y = torch.empty_like(x)
 dx, dy = ae.DeviceVec.from_torch(x), ae.DeviceVec.from_torch(y)
-for name, t, mode in (("direct64", 64, F.DIRECT), ("os64", 64, F.OVERLAP_SAVE), ("os1024", 1024, F.OVERLAP_SAVE), ("direct16", 16, F.DIRECT)):
+cases = [("direct64", 64, F.DIRECT), ("os64", 64, F.OVERLAP_SAVE), ("os1024", 1024, F.OVERLAP_SAVE)]
+if len(sys.argv) > 2:   # threshold sweep: direct vs overlap-save for short filters
+    cases = [(("direct%d" if m == F.DIRECT else "os%d") % t, t, m) for t in (2, 4, 6, 8, 12, 16, 24, 32) for m in (F.DIRECT, F.OVERLAP_SAVE)]
+for name, t, mode in cases:
     filt = F.Fir(make_taps(t), mode)
     for _ in range(3):
         filt.filter(dx, dy)
