@@ -380,8 +380,14 @@ __device__ __forceinline__ void gen_butterfly_pass(const float2* src, float2* ds
       if (conj_in) v[r].y = -v[r].y;
     }
     if (ns > 1) {
+      // W^(r k tws), r = 1..P-1: one table read, the higher powers as balanced products (the pass is bound
+      // by the L1/shared-memory pipe, not by FP32 issue; each product costs about one ulp)
+      float2 w[P];
+      w[1] = __ldg(tw + k * tws);
 #pragma unroll
-      for (int r = 1; r < P; ++r) v[r] = cx_mul(v[r], __ldg(tw + r * k * tws));   // r*k*tws < n
+      for (int r = 2; r < P; ++r) w[r] = cx_mul(w[r / 2], w[r - r / 2]);
+#pragma unroll
+      for (int r = 1; r < P; ++r) v[r] = cx_mul(v[r], w[r]);
     }
     if constexpr (P & 1) odd_dft<P>(v, root);
     else Dft<P, false>::run(v);
