@@ -312,13 +312,13 @@ ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int tw
     //      GF(2): word t of the sequence started from `state` is the XOR, over the set bits i of the
     //      state, of word t of the sequence started from the unit state e_i (host table zcol[i][t]) ----
     {
-      uint32_t state = (uint32_t)((frame_id + 1) & 0x7fffffffull);  // expand(frame_id+1, 31)
+      const uint32_t state = (uint32_t)((frame_id + 1) & 0x7fffffffull);  // expand(frame_id+1, 31)
       uint32_t w = 0;
-      while (state) {  // uniform across the slot: one iteration per set seed bit
-        const int i = __ffs(state) - 1;
-        w ^= __ldg(zcol + i * C::T + t);
-        state &= state - 1;
-      }
+      // one predicated, independent load per seed bit (the bit test is uniform across the slot); a
+      // find-first-set loop chained every table read behind the previous one (11 % of the stall samples)
+#pragma unroll
+      for (int i = 0; i < 31; ++i)
+        if ((state >> i) & 1u) w ^= __ldg(zcol + i * C::T + t);
       words[t] = w;
     }
     frame_sync<C::T>(f);

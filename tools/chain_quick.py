@@ -12,8 +12,8 @@ import aether_primitives_b200 as ae
 from aether_primitives_b200.chain import FftFirDemod
 from bench import make_taps
 
-frames = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 19
-n = 1024
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else (1 << 29) // int(os.environ.get("NFFT", "1024"))
+n = int(os.environ.get("NFFT", "1024"))
 ae.init(0)
 ae.use_torch_stream()
 x = torch.view_as_complex(torch.randn(frames * n, 2, device="cuda"))
