@@ -300,7 +300,12 @@ ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int tw
   unsigned char* my = smem_raw + (size_t)f * LC::SMEM_PER_FRAME;
   float2* sm = reinterpret_cast<float2*>(my);
   uint32_t* words = reinterpret_cast<uint32_t*>(my + (size_t)C::SMEM_ELEMS * sizeof(float2));
-  const float2 tab[4] = {make_float2(1.0f, 1.0f), make_float2(-1.0f, 1.0f), make_float2(1.0f, -1.0f), make_float2(-1.0f, -1.0f)};
+  // QPSK table (src/modulation.rs:87-92) 0:(1,1) 1:(-1,1) 2:(1,-1) 3:(-1,-1): re = +-1 by bit 0, im = +-1 by
+  // bit 1 of the index, so the symbol is 1.0f with the index bits moved into the sign bits (an indexed
+  // local table compiled into four compares and eight predicated moves per symbol)
+  auto qpsk_symbol = [](unsigned two) {
+    return make_float2(__uint_as_float(0x3f800000u | ((two & 1u) << 31)), __uint_as_float(0x3f800000u | ((two >> 1) << 31)));
+  };
   const float sn = 1.0f / sqrtf((float)N);  // Scale::SN (src/fft.rs:26)
   const unsigned hi_shift = compat == AE_COMPAT_REFERENCE ? 9u : 8u;
   unsigned long long errs = 0;
@@ -331,7 +336,7 @@ ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int tw
       const uint32_t w = words[pos >> 4];
       const unsigned two = (w >> ((2 * pos) & 31)) & 3u;  // bit0 = b0, bit1 = b1 -> idx = (b1<<1)+b0
       txb |= two << (2 * m);
-      v[m] = tab[two];
+      v[m] = qpsk_symbol(two);
     }
     if (tx_bits) {
       uint16_t* o = reinterpret_cast<uint16_t*>(tx_bits + 2 * fl * (size_t)N);
@@ -366,7 +371,8 @@ ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int tw
       const unsigned two = (txb >> (2 * m)) & 3u;
       if (!qpsk_fast_ok(v[m])) risky |= 1u << m;
       rxb |= ((__float_as_uint(v[m].x) >> 31) | ((__float_as_uint(v[m].y) >> 31) << 1)) << (2 * m);
-      const float dr = v[m].x - tab[two].x, di = v[m].y - tab[two].y;
+      const float2 ref = qpsk_symbol(two);
+      const float dr = v[m].x - ref.x, di = v[m].y - ref.y;
       e_pow += dr * dr + di * di;
     }
     if (risky) {
