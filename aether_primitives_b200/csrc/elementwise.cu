@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(256) modem_kernel(const __grid_constant__ ModT
       if (BPS == 1) idx = bi[i];
       else idx = (uint8_t)((uint8_t)(bi[2 * i + 1] << 1) + bi[2 * i]);
       float2 s = make_float2(0.0f, 0.0f);
-      if (idx < (unsigned)M) s = tab[idx];
+      if (idx < (unsigned)M) s = tabp.t[idx];   // indexed read of the constant bank (tab[] is a register copy for demod)
       else if (ok) atomicOr(errflag, DEVERR_MOD_INDEX);
       float2 nz = cx_scale_exact(z[i], scale);
       if (twice) nz = cx_scale_exact(nz, scale);
