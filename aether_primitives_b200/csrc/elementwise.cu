@@ -10,6 +10,8 @@
 //   K13 bit-error / EVM partial sums
 // All float arithmetic that the reference's tests pin exactly uses the *_exact helpers
 // (no FMA contraction, IEEE division, denormals kept).
+#include <type_traits>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -404,7 +406,8 @@ __global__ void __launch_bounds__(256) modem_kernel(const __grid_constant__ ModT
   const uint64_t p0 = offset >> 1;
   const uint64_t npairs = ((offset + nsym + 1) >> 1) - p0;
   for (uint64_t q = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 2; q < npairs; q += (uint64_t)gridDim.x * 512) {
-    uint8_t bi[4 * BPS], bo[4 * BPS];
+    alignas(8) uint8_t bi[4 * BPS];
+    alignas(8) uint8_t bo[4 * BPS];
     const uint64_t g0 = 2 * (p0 + q);           // global index of the first of 4 samples
     const long long l0 = (long long)(g0 - offset);  // local symbol index (may be -1)
     const bool full = vec_ok && l0 >= 0 && (size_t)(l0 + 4) <= nsym;
@@ -423,24 +426,42 @@ __global__ void __launch_bounds__(256) modem_kernel(const __grid_constant__ ModT
     float2 z[4];
     awgn_unit_pair(keys, stream, p0 + q, z[0], z[1]);
     awgn_unit_pair(keys, stream, p0 + q + 1, z[2], z[3]);
+    // CHECKED = false: all four symbols exist (the common case) - no per-symbol bounds tests, bit errors
+    // counted on the packed bytes afterwards
+    auto body = [&](auto checked_tag) {
+      constexpr bool CHECKED = decltype(checked_tag)::value;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long l = l0 + i;
-      const bool ok = l >= 0 && (size_t)l < nsym;
-      unsigned idx;
-      if (BPS == 1) idx = bi[i];
-      else idx = (uint8_t)((uint8_t)(bi[2 * i + 1] << 1) + bi[2 * i]);
-      float2 s = make_float2(0.0f, 0.0f);
-      if (idx < (unsigned)M) s = tabp.t[idx];   // indexed read of the constant bank (tab[] is a register copy for demod)
-      else if (ok) atomicOr(errflag, DEVERR_MOD_INDEX);
-      float2 nz = cx_scale_exact(z[i], scale);
-      if (twice) nz = cx_scale_exact(nz, scale);
-      s = cx_add_exact(s, nz);
-      demod_emit<M>(s, tab, compat, bo + i * BPS, generic);
-      if (ok) {
+      for (int i = 0; i < 4; ++i) {
+        const long long l = l0 + i;
+        const bool ok = !CHECKED || (l >= 0 && (size_t)l < nsym);
+        unsigned idx;
+        if (BPS == 1) idx = bi[i];
+        else idx = (uint8_t)((uint8_t)(bi[2 * i + 1] << 1) + bi[2 * i]);
+        float2 s = make_float2(0.0f, 0.0f);
+        if (idx < (unsigned)M) s = tabp.t[idx];   // indexed read of the constant bank (tab[] is a register copy for demod)
+        else if (ok) atomicOr(errflag, DEVERR_MOD_INDEX);
+        float2 nz = cx_scale_exact(z[i], scale);
+        if (twice) nz = cx_scale_exact(nz, scale);
+        s = cx_add_exact(s, nz);
+        demod_emit<M>(s, tab, compat, bo + i * BPS, generic);
+        if (CHECKED && ok) {
 #pragma unroll
-        for (int b = 0; b < BPS; ++b) errs += ((bi[i * BPS + b] != 0) != (bo[i * BPS + b] != 0));
+          for (int b = 0; b < BPS; ++b) errs += ((bi[i * BPS + b] != 0) != (bo[i * BPS + b] != 0));
+        }
       }
+    };
+    if (full) {
+      body(std::false_type{});
+      // a bit is in error when exactly one of (sent, received) is non-zero: compare the non-zero masks
+      if (BPS == 2) {
+        const uint2 a = *reinterpret_cast<const uint2*>(bi), b = *reinterpret_cast<const uint2*>(bo);
+        errs += (__popc(__vcmpne4(a.x, 0u) ^ __vcmpne4(b.x, 0u)) + __popc(__vcmpne4(a.y, 0u) ^ __vcmpne4(b.y, 0u))) >> 3;
+      } else {
+        const uint32_t a = *reinterpret_cast<const uint32_t*>(bi), b = *reinterpret_cast<const uint32_t*>(bo);
+        errs += __popc(__vcmpne4(a, 0u) ^ __vcmpne4(b, 0u)) >> 3;
+      }
+    } else {
+      body(std::true_type{});
     }
     if (full) {
       if (BPS == 2) __stcs(reinterpret_cast<uint2*>(bout + l0 * 2), *reinterpret_cast<uint2*>(bo));
