@@ -224,25 +224,41 @@ fir_os_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_t n, co
     out_end = out_start + L < (long long)n ? out_start + L : (long long)n;
   }
   const long long in_start = out_start - (ntaps - 1);
+  // interior segment: every input exists inside the frame and every output is kept, so neither the
+  // loads nor the stores need per-element bounds tests (they were 20 % of the executed instructions)
+  const bool interior = in_start >= frame_start && out_end == out_start + L;
   float2 v[16];
+  if (interior) {
+    const float2* src = x + in_start + t;
 #pragma unroll
-  for (int m = 0; m < 16; ++m) {
-    const long long g = in_start + t + m * C::T;
-    float2 s = make_float2(0.0f, 0.0f);
-    if (g >= frame_start) { if (g < out_end) s = ld_stream(x + g); }
-    else if (!frame_len && history && g >= -(long long)hist_len) s = __ldg(history + hist_len + g);
-    v[m] = s;
+    for (int m = 0; m < 16; ++m) v[m] = ld_stream(src + m * C::T);
+  } else {
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const long long g = in_start + t + m * C::T;
+      float2 s = make_float2(0.0f, 0.0f);
+      if (g >= frame_start) { if (g < out_end) s = ld_stream(x + g); }
+      else if (!frame_len && history && g >= -(long long)hist_len) s = __ldg(history + hist_len + g);
+      v[m] = s;
+    }
   }
   fft_frame<NF, false>(v, sm, tw, t, f);
 #pragma unroll
   for (int m = 0; m < 16; ++m) v[m] = cx_mul(v[m], __ldg(H + t + m * C::T));
   frame_sync<C::T>(f);  // every thread is past its last read of sm
   fft_frame<NF, true>(v, sm, tw, t, f);
+  if (interior) {
+    float2* dst = y + in_start + t;
 #pragma unroll
-  for (int m = 0; m < 16; ++m) {
-    const int i = t + m * C::T;
-    const long long g = out_start + i - (ntaps - 1);
-    if (i >= ntaps - 1 && g < out_end) st_stream(y + g, v[m]);
+    for (int m = 0; m < 16; ++m)
+      if (t + m * C::T >= ntaps - 1) st_stream(dst + m * C::T, v[m]);
+  } else {
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int i = t + m * C::T;
+      const long long g = out_start + i - (ntaps - 1);
+      if (i >= ntaps - 1 && g < out_end) st_stream(y + g, v[m]);
+    }
   }
 }
 
