@@ -716,35 +716,60 @@ __device__ __forceinline__ StatPart stat_block_fold(StatPart p) {
   return p;
 }
 
+// Per thread: elements i0 + it*stride, it = 0, 1, ...  The streaming loop keeps (min, max) with 32-bit
+// iteration counters and plain `<` / `>` tests against +inf / -inf (NaN never passes either test); an
+// element equal to the initial bound cannot win that way, so a thread that ends without a minimum or a
+// maximum (its elements were all NaN / +-inf) re-walks its elements with the exact first-comparable rule.
 template <bool CPLX>
-__device__ __forceinline__ void stat_take(StatPart& p, const void* base, size_t i) {
-  float v;
+__device__ __forceinline__ float stat_value(const void* base, size_t i, double& sre, double& sim, double& spow) {
   if (CPLX) {
     const float2 x = __ldcs((const float2*)base + i);
-    v = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
-    p.sre += (double)x.x; p.sim += (double)x.y; p.spow += (double)x.x * (double)x.x + (double)x.y * (double)x.y;
+    sre += (double)x.x; sim += (double)x.y; spow += (double)x.x * (double)x.x + (double)x.y * (double)x.y;
+    return __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
   } else {
-    v = __ldcs((const float*)base + i);
-    p.sre += (double)v; p.spow += (double)v * (double)v;
-  }
-  if (v == v) {                                   // NaN is never a minimum or a maximum
-    if (p.imn == STAT_NONE || v < p.mn) { p.mn = v; p.imn = i; }
-    if (p.imx == STAT_NONE || v > p.mx) { p.mx = v; p.imx = i; }
+    const float v = __ldcs((const float*)base + i);
+    sre += (double)v; spow += (double)v * (double)v;
+    return v;
   }
 }
 
 template <bool CPLX>
 __global__ void __launch_bounds__(256) vecstats_kernel(const void* __restrict__ v, size_t n, StatPart* __restrict__ parts) {
-  StatPart p{0.0, 0.0, 0.0, 0.f, 0.f, STAT_NONE, STAT_NONE};
+  constexpr unsigned NONE32 = 0xffffffffu;
   const size_t stride = (size_t)gridDim.x * 256;
-  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-  for (; i + 3 * stride < n; i += 4 * stride) {   // four independent loads in flight
-    stat_take<CPLX>(p, v, i);
-    stat_take<CPLX>(p, v, i + stride);
-    stat_take<CPLX>(p, v, i + 2 * stride);
-    stat_take<CPLX>(p, v, i + 3 * stride);
+  const size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x;
+  double sre = 0.0, sim = 0.0, spow = 0.0;
+  float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+  unsigned itmn = NONE32, itmx = NONE32, it = 0;
+  size_t i = i0;
+  for (; i + 3 * stride < n; i += 4 * stride, it += 4) {   // four independent loads in flight
+    float a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = stat_value<CPLX>(v, i + u * stride, sre, sim, spow);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (a[u] < mn) { mn = a[u]; itmn = it + u; }
+      if (a[u] > mx) { mx = a[u]; itmx = it + u; }
+    }
   }
-  for (; i < n; i += stride) stat_take<CPLX>(p, v, i);
+  for (; i < n; i += stride, ++it) {
+    const float a = stat_value<CPLX>(v, i, sre, sim, spow);
+    if (a < mn) { mn = a; itmn = it; }
+    if (a > mx) { mx = a; itmx = it; }
+  }
+  StatPart p{sre, sim, spow, mn, mx, itmn == NONE32 ? STAT_NONE : i0 + (size_t)itmn * stride,
+             itmx == NONE32 ? STAT_NONE : i0 + (size_t)itmx * stride};
+  if ((itmn == NONE32 || itmx == NONE32) && i0 < n) {       // rare: only NaN / infinities seen by this thread
+    p.imn = p.imx = STAT_NONE;
+    for (size_t j = i0; j < n; j += stride) {
+      double d0 = 0, d1 = 0, d2 = 0;
+      const float a = stat_value<CPLX>(v, j, d0, d1, d2);
+      if (a == a) {
+        if (p.imn == STAT_NONE || a < p.mn) { p.mn = a; p.imn = j; }
+        if (p.imx == STAT_NONE || a > p.mx) { p.mx = a; p.imx = j; }
+      }
+    }
+  }
   p = stat_block_fold(p);
   if (threadIdx.x == 0) parts[blockIdx.x] = p;
 }
