@@ -454,7 +454,13 @@ __device__ __forceinline__ void gen_pass(const GenPass& gp, unsigned mg_n, const
   }
 }
 
-__global__ void __launch_bounds__(256, 3) fft_generic_smem_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+#ifndef AE_GEN_MINB
+#define AE_GEN_MINB 3
+#endif
+#ifndef AE_GEN_ELEMS
+#define AE_GEN_ELEMS 4096
+#endif
+__global__ void __launch_bounds__(256, AE_GEN_MINB) fft_generic_smem_kernel(const float2* __restrict__ in, float2* __restrict__ out,
                                                                const float2* __restrict__ tw, unsigned n, size_t frames, unsigned slots,
                                                                const __grid_constant__ GenRadices rad, int inverse, int do_scale,
                                                                float scale) {
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(256, 3) fft_generic_smem_kernel(const float2* 
 }
 
 static unsigned gen_slots(size_t n) {
-  size_t s = 4096 / n;
+  size_t s = AE_GEN_ELEMS / n;
   return (unsigned)(s < 1 ? 1 : (s > 64 ? 64 : s));
 }
 
