@@ -528,6 +528,7 @@ __device__ __forceinline__ uint64_t gf2_mulmod(uint64_t a, uint64_t b, uint64_t 
 }
 constexpr int kMseqBitsPerThread = 512;
 constexpr int kMseqThreads = 128;
+constexpr int kMseqPitch = kMseqThreads + 2;   // half-words per 16-bit group row in shared memory
 struct MseqTables {
   uint64_t pow2[64];              // z^(2^i) mod p
   uint64_t thread[kMseqThreads];  // z^(kMseqBitsPerThread * t) mod p
@@ -539,9 +540,9 @@ __device__ __forceinline__ uint32_t spread4(uint32_t b) { return ((b & 0xfu) * 0
 // and x[0..deg) = state bits.  Jump-ahead: z^n mod p(z) = sum c_i z^i  =>  x[n] = parity(c & state).
 // Block start: product of the host-tabulated z^(2^i) over the set bits of the offset (thread 0);
 // thread start: one more multiplication with the tabulated z^(512 t); then 512 bits per thread from a
-// 64-bit sliding window, written as 16-byte vectors.
-__global__ void __launch_bounds__(kMseqThreads) mseq_kernel(uint64_t state, uint64_t poly_low, int deg, size_t len, uint8_t* __restrict__ out,
-                                                            const __grid_constant__ MseqTables tab) {
+// 64-bit sliding window, packed 16 to a half-word in shared memory and expanded by the whole CTA.
+__device__ __forceinline__ void mseq_fill_bits(uint64_t state, uint64_t poly_low, int deg, size_t len, const MseqTables& tab,
+                                               uint16_t* s_bits) {
   __shared__ uint64_t s_block;
   const size_t block_start = (size_t)blockIdx.x * kMseqThreads * kMseqBitsPerThread;
   if (threadIdx.x == 0) {
@@ -564,24 +565,53 @@ __global__ void __launch_bounds__(kMseqThreads) mseq_kernel(uint64_t state, uint
     r = (deg == 64) ? (r << 1) : ((r << 1) & ((1ull << deg) - 1ull));
     if (carry) r ^= poly_low;
   }
-  // emit: window holds x[n .. n+deg) for the current n
+  // emit: window holds x[n .. n+deg) for the current n.  A thread owns 512 consecutive bits, so storing
+  // its bytes directly would scatter every warp store over 32 lines; the packed bits go to shared memory
+  // (16 per half-word) and the CTA then expands them with fully coalesced 16-byte stores.
   const size_t end = (n0 + kMseqBitsPerThread < len) ? n0 + kMseqBitsPerThread : len;
-  const bool vec_ok = ((uintptr_t)out % 16) == 0;
-  size_t n = n0;
-  while (n < end) {
-    uint32_t b16 = 0;
-    const int cnt = (end - n) >= 16 ? 16 : (int)(end - n);
-    for (int i = 0; i < cnt; ++i) {
-      b16 |= (uint32_t)(window & 1ull) << i;
-      const uint64_t nb = (uint64_t)(__popcll(window & poly_low) & 1);
-      window = (window >> 1) | (nb << (deg - 1));
-    }
-    if (cnt == 16 && vec_ok) {
-      *reinterpret_cast<uint4*>(out + n) = make_uint4(spread4(b16), spread4(b16 >> 4), spread4(b16 >> 8), spread4(b16 >> 12));
+  // When every tap reaches back at least 16 elements (LTE x1: 28 and 31), the next 16 elements depend only
+  // on elements already in the window: x[n+i] = XOR_t x[n+i-back_t] for i < 16 is the XOR of the window
+  // shifted by (deg - back_t) - sixteen sequence elements per step instead of one.
+  int top_tap = 63;
+  while (top_tap > 0 && !((poly_low >> top_tap) & 1ull)) --top_tap;       // deg - (smallest back offset)
+  const bool wide = deg >= 16 && deg - top_tap >= 16;
+  for (int g16 = 0; g16 < kMseqBitsPerThread / 16; ++g16) {
+    uint32_t b16;
+    if (wide) {
+      b16 = (uint32_t)window & 0xffffu;
+      uint64_t nw = 0;
+      for (uint64_t m = poly_low; m; m &= m - 1) nw ^= window >> (__ffsll((long long)m) - 1);
+      window = (window >> 16) | ((nw & 0xffffull) << (deg - 16));
     } else {
-      for (int i = 0; i < cnt; ++i) out[n + i] = (uint8_t)((b16 >> i) & 1u);
+      b16 = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        b16 |= (uint32_t)(window & 1ull) << i;
+        const uint64_t nb = (uint64_t)(__popcll(window & poly_low) & 1);
+        window = (window >> 1) | (nb << (deg - 1));
+      }
     }
-    n += cnt;
+    s_bits[g16 * kMseqPitch + threadIdx.x] = (uint16_t)b16;   // [group][thread], pitch 130: conflict-free both ways
+    if (n0 + 16 * (size_t)(g16 + 1) >= end) break;       // nothing of this thread's run lies beyond len
+  }
+}
+
+__global__ void __launch_bounds__(kMseqThreads) mseq_kernel(uint64_t state, uint64_t poly_low, int deg, size_t len, uint8_t* __restrict__ out,
+                                                            const __grid_constant__ MseqTables tab) {
+  __shared__ uint16_t s_bits[(kMseqBitsPerThread / 16) * kMseqPitch];
+  mseq_fill_bits(state, poly_low, deg, len, tab, s_bits);
+  __syncthreads();
+  const size_t block_start = (size_t)blockIdx.x * kMseqThreads * kMseqBitsPerThread;
+  const bool vec_ok = ((uintptr_t)out % 16) == 0;
+  for (int q = threadIdx.x; q < kMseqThreads * kMseqBitsPerThread / 16; q += kMseqThreads) {
+    const size_t n = block_start + 16 * (size_t)q;
+    if (n >= len) break;
+    const uint32_t b16 = s_bits[(q % (kMseqBitsPerThread / 16)) * kMseqPitch + q / (kMseqBitsPerThread / 16)];
+    if (n + 16 <= len && vec_ok) {
+      __stcs(reinterpret_cast<uint4*>(out + n), make_uint4(spread4(b16), spread4(b16 >> 4), spread4(b16 >> 8), spread4(b16 >> 12)));
+    } else {
+      for (int i = 0; i < 16 && n + i < len; ++i) out[n + i] = (uint8_t)((b16 >> i) & 1u);
+    }
   }
 }
 static uint64_t host_gf2_mulmod(uint64_t a, uint64_t b, uint64_t poly_low, int deg) {

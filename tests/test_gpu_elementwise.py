@@ -177,7 +177,8 @@ def test_sequence_golden(ae):
         ae.sequence.expand(1, 65)
 
 
-@pytest.mark.parametrize("back", [[1, 2], [28, 31], [3, 31], [1, 3, 4, 64], [5, 5, 7], [1], [63], [2, 4, 6]])
+@pytest.mark.parametrize("back", [[1, 2], [28, 31], [3, 31], [1, 3, 4, 64], [5, 5, 7], [1], [63], [2, 4, 6],
+                                  [16], [16, 17], [16, 64], [20, 33, 64], [17, 17, 40], [15, 31], [64]])  # >= 16 everywhere: 16 elements per step
 @pytest.mark.parametrize("length", [10, 100, 32769, 300007])
 def test_mseq_vs_oracle(ae, back, length):
     rng = np.random.default_rng(sum(back) + length)
