@@ -11,12 +11,12 @@ from .runtime import init, sync, set_stream, device_count, launch_count, sm_coun
 from .vecops import DeviceVec, DeviceBits
 from .fft import Scale, Cfft
 from .fir import Fir
-from . import sampling, modulation, noise, sequence, chain, stats, spectral
+from . import sampling, modulation, noise, sequence, chain, stats, spectral, util
 
 cf32 = "complex64"  # numpy dtype of the reference's cf32 (src/lib.rs:12)
 
 __all__ = [
     "AeError", "COMPAT_REFERENCE", "COMPAT_CORRECTED", "init", "sync", "set_stream", "device_count",
     "launch_count", "sm_count", "use_torch_stream", "DeviceVec", "DeviceBits", "Scale", "Cfft", "Fir",
-    "sampling", "modulation", "noise", "sequence", "chain", "stats", "spectral", "cf32",
+    "sampling", "modulation", "noise", "sequence", "chain", "stats", "spectral", "util", "cf32",
 ]

@@ -12,6 +12,7 @@
 // A Rust panic becomes an aether::Panic exception carrying the reference's message.
 // Header-only; link with libaether_b200.so.  (INTEGRATION.md shows the Rust binding.)
 #pragma once
+#include <cmath>
 #include <complex>
 #include <cstdint>
 #include <stdexcept>
@@ -289,6 +290,14 @@ class ChainPipeline {
 
  private:
   ae_pipe* h_ = nullptr;
+};
+
+/// util::DB (src/util/mod.rs:11-46): a value in decibel; DB::from(ratio) = 10 log10(ratio) in f64
+struct DB {
+  double value;
+  static DB from(double ratio) { return DB{10.0 * std::log10(ratio)}; }
+  double db() const { return value; }
+  double ratio() const { return std::pow(10.0, value / 10.0); }
 };
 
 }  // namespace aether

@@ -85,3 +85,14 @@ def test_rust_sys_binding_is_generated_from_the_current_header():
 
     text = open(os.path.join(root, "rust", "aether-b200-sys", "src", "lib.rs")).read()
     assert set(re.findall(r"pub fn (ae_\w+)\(", text)) == set(_lib.EXPORTS)
+
+
+def test_util_db_matches_the_reference_tests():
+    """src/util/mod.rs:14-22 (doctest) and :53-66 (db_to_ratio, ratio_to_db)."""
+    from aether_primitives_b200.util import DB
+
+    db = DB.from_ratio(100)
+    assert db.ratio() == 100.0 and db.db() == 20.0
+    assert DB(30.0).ratio() == 1000.0 and DB(0.0).ratio() == 1.0
+    assert abs(DB.from_ratio(100.0).db() - 20.0) < 1e-6 and abs(DB.from_ratio(0.1).db() + 10.0) < 1e-6
+    assert DB.from_ratio(0.0).db() == float("-inf")
