@@ -128,6 +128,21 @@ class DeviceVec:
         """util::file::binary_writer::<cf32> (src/util/file.rs:72-107)."""
         call("ae_vec_write_raw", self._h, path.encode())
 
+    @classmethod
+    def from_csv(cls, path: str) -> "DeviceVec":
+        """util::file::csv_reader for cf32 (src/util/file.rs:117-124): one `re,im` record per line, no header."""
+        a = np.loadtxt(path, delimiter=",", dtype=np.float32, ndmin=2)
+        if a.size and a.shape[1] != 2:
+            raise _lib.AeError(_lib.AE_EARG, "CSV deserialize error: expected 2 fields per record")
+        return cls.from_numpy((a[:, 0] + 1j * a[:, 1]).astype(np.complex64) if a.size else np.zeros(0, np.complex64))
+
+    def to_csv(self, path: str) -> None:
+        """util::file::csv_writer for cf32 (src/util/file.rs:109-116): `re,im` per line, no header."""
+        x = self.to_numpy()
+        with open(path, "w") as f:
+            for v in x:
+                f.write("%s,%s\n" % (repr(float(np.float32(v.real))), repr(float(np.float32(v.imag)))))
+
     def vec_stats(self):
         """VecStats over the vector (pending VecOps are flushed first); see `stats.VecStats`."""
         from .stats import VecStats

@@ -126,3 +126,14 @@ def test_empty_inputs_behave_like_empty_slices(ae):
     ch.run(e, bits)                                           # zero frames
     assert len(bits) == 0
     assert len(ae.sequence.expand(5, 0)) == 0
+
+
+def test_csv_round_trip(ae, tmp_path):
+    """util::file csv reader/writer for cf32 (src/util/file.rs:109-124, test :176-214): `re,im` per line, no header."""
+    x = (np.arange(200) + 1j * np.arange(200)).astype(np.complex64)          # the reference test's sequence
+    x[7] = complex(np.float32(0.1), np.float32(-1e-7))
+    p = str(tmp_path / "seq.csv")
+    ae.DeviceVec.from_numpy(x).to_csv(p)
+    assert open(p).readline().strip() == "0.0,0.0"
+    back = ae.DeviceVec.from_csv(p).to_numpy()
+    assert back.tobytes() == x.tobytes()
