@@ -215,7 +215,19 @@ __global__ void __launch_bounds__(256) interpolate_kernel(const float2* __restri
     const float r1 = __fdiv_rn(__fsub_rn(x2.y, x1.y), div);
     const float imb = compat == AE_COMPAT_REFERENCE ? x1.x : x1.y;  // :19 uses x1.re
     float2* o = dst + w * (size_t)K1;
-    if (K1T > 0 && (K1T % 2) == 0 && vec_ok) {
+    if (K1T == 4 && vec_ok == 2) {
+      // 32 bytes per window: one 256-bit store (sm_100 STG.256), so a warp store covers 1 KiB contiguously
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float f = (float)i;
+        v[2 * i] = __fadd_rn(x1.x, __fmul_rn(f, r0));
+        v[2 * i + 1] = __fadd_rn(imb, __fmul_rn(f, r1));
+      }
+      asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                   "f"(v[5]), "f"(v[6]), "f"(v[7])
+                   : "memory");
+    } else if (K1T > 0 && (K1T % 2) == 0 && vec_ok) {
 #pragma unroll
       for (int i = 0; i < K1T; i += 2) {
         const float f0 = (float)i, f1 = (float)(i + 1);
@@ -236,7 +248,7 @@ __global__ void __launch_bounds__(256) interpolate_kernel(const float2* __restri
 void launch_interpolate(const float2* src, size_t n_src, float2* dst, size_t n_between, int compat, cudaStream_t st) {
   if (n_src == 0) return;
   const int k1 = (int)(n_between + 1);
-  const int vec_ok = ((uintptr_t)dst % 16) == 0;
+  const int vec_ok = ((uintptr_t)dst % 32) == 0 ? 2 : (((uintptr_t)dst % 16) == 0 ? 1 : 0);   // 2: 256-bit stores allowed
   const unsigned g = cdiv(n_src, 256);
   if (k1 == 4) interpolate_kernel<4><<<g, 256, 0, st>>>(src, n_src, dst, k1, compat, vec_ok);
   else if (k1 == 2) interpolate_kernel<2><<<g, 256, 0, st>>>(src, n_src, dst, k1, compat, vec_ok);
