@@ -202,4 +202,12 @@ __device__ __forceinline__ void awgn_unit_pair(const PhiloxKeys& keys, uint64_t 
   z1 = gauss_pair(o[2], o[3]);
 }
 
+// 256-bit streaming store (sm_100: STG.256): 32 bytes per lane, so a warp store covers 1 KiB contiguously.
+// p must be 32-byte aligned.
+__device__ __forceinline__ void st_stream_256(void* p, float4 a, float4 b) {
+  asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y),
+               "f"(b.z), "f"(b.w)
+               : "memory");
+}
+
 }  // namespace ae

@@ -224,9 +224,7 @@ __global__ void __launch_bounds__(256) interpolate_kernel(const float2* __restri
         v[2 * i] = __fadd_rn(x1.x, __fmul_rn(f, r0));
         v[2 * i + 1] = __fadd_rn(imb, __fmul_rn(f, r1));
       }
-      asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
-                   "f"(v[5]), "f"(v[6]), "f"(v[7])
-                   : "memory");
+      st_stream_256(o, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
     } else if (K1T > 0 && (K1T % 2) == 0 && vec_ok) {
 #pragma unroll
       for (int i = 0; i < K1T; i += 2) {
@@ -281,15 +279,19 @@ __global__ void __launch_bounds__(256) modulate_kernel(const __grid_constant__ M
 #pragma unroll
     for (int i = 0; i < 4; ++i) s[i] = mod_symbol<BPS>(tab, b + i * BPS, errflag);
     float4* o = reinterpret_cast<float4*>(out + s0);
-    __stcs(o, make_float4(s[0].x, s[0].y, s[1].x, s[1].y));
-    __stcs(o + 1, make_float4(s[2].x, s[2].y, s[3].x, s[3].y));
+    if (vec_ok == 2) {
+      st_stream_256(o, make_float4(s[0].x, s[0].y, s[1].x, s[1].y), make_float4(s[2].x, s[2].y, s[3].x, s[3].y));
+    } else {
+      __stcs(o, make_float4(s[0].x, s[0].y, s[1].x, s[1].y));
+      __stcs(o + 1, make_float4(s[2].x, s[2].y, s[3].x, s[3].y));
+    }
   } else {
     for (size_t s = s0; s < n_out && s < s0 + 4; ++s) out[s] = mod_symbol<BPS>(tab, bits + s * BPS, errflag);
   }
 }
 void launch_modulate(const ModTable& tab, const uint8_t* bits, size_t, float2* out, size_t n_out, int* errflag, cudaStream_t st) {
   if (n_out == 0) return;
-  const int vec_ok = ((uintptr_t)bits % 8) == 0 && ((uintptr_t)out % 16) == 0;
+  const int vec_ok = (((uintptr_t)bits % 8) == 0 && ((uintptr_t)out % 16) == 0) ? (((uintptr_t)out % 32) == 0 ? 2 : 1) : 0;   // 2: 256-bit stores
   const unsigned g = cdiv(cdiv(n_out, 4), 256);
   if (tab.len == 2) modulate_kernel<1><<<g, 256, 0, st>>>(tab, bits, out, n_out, vec_ok, errflag);
   else modulate_kernel<2><<<g, 256, 0, st>>>(tab, bits, out, n_out, vec_ok, errflag);
@@ -344,35 +346,43 @@ void launch_demod(const ModTable& tab, const float2* sym, size_t n, uint8_t* bit
 template <bool APPLY>
 __global__ void __launch_bounds__(256) awgn_kernel(float2* __restrict__ buf, size_t n, float scale, int twice,
                                                    const __grid_constant__ PhiloxKeys keys, uint64_t stream, uint64_t offset, int vec_ok) {
-  const uint64_t p0 = offset >> 1;
-  const uint64_t P = p0 + (uint64_t)blockIdx.x * 256 + threadIdx.x;
-  const uint64_t g0 = 2 * P, g1 = g0 + 1;
+  // thread = two consecutive Philox blocks = the four samples 4Q .. 4Q+3 of the stream (32 bytes)
+  const uint64_t q0 = offset >> 2;
+  const uint64_t Q = q0 + (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const uint64_t g0 = 4 * Q;
   if (g0 >= offset + n) return;
-  float2 z0, z1;
-  awgn_unit_pair(keys, stream, P, z0, z1);
+  float2 z[4];
+  awgn_unit_pair(keys, stream, 2 * Q, z[0], z[1]);
+  awgn_unit_pair(keys, stream, 2 * Q + 1, z[2], z[3]);
   // next(): (N(0,1) as f32) * scale (:41-42); apply(): ... .scale(sc) once more (:58)
-  z0 = cx_scale_exact(z0, scale); z1 = cx_scale_exact(z1, scale);
-  if (twice) { z0 = cx_scale_exact(z0, scale); z1 = cx_scale_exact(z1, scale); }
-  const bool in0 = g0 >= offset, in1 = g1 < offset + n;
-  if (vec_ok && in0 && in1) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    z[i] = cx_scale_exact(z[i], scale);
+    if (twice) z[i] = cx_scale_exact(z[i], scale);
+  }
+  if (vec_ok && g0 >= offset && g0 + 4 <= offset + n) {
     float4* q = reinterpret_cast<float4*>(buf + (g0 - offset));
+    float4 a = make_float4(z[0].x, z[0].y, z[1].x, z[1].y), b = make_float4(z[2].x, z[2].y, z[3].x, z[3].y);
     if (APPLY) {
-      const float4 s = __ldcs(q);
-      __stcs(q, make_float4(__fadd_rn(s.x, z0.x), __fadd_rn(s.y, z0.y), __fadd_rn(s.z, z1.x), __fadd_rn(s.w, z1.y)));
-    } else {
-      __stcs(q, make_float4(z0.x, z0.y, z1.x, z1.y));
+      const float4 s0 = __ldcs(q), s1 = __ldcs(q + 1);
+      a = make_float4(__fadd_rn(s0.x, a.x), __fadd_rn(s0.y, a.y), __fadd_rn(s0.z, a.z), __fadd_rn(s0.w, a.w));
+      b = make_float4(__fadd_rn(s1.x, b.x), __fadd_rn(s1.y, b.y), __fadd_rn(s1.z, b.z), __fadd_rn(s1.w, b.w));
     }
+    st_stream_256(q, a, b);
   } else {
-    if (in0) { float2* q = buf + (g0 - offset); *q = APPLY ? cx_add_exact(*q, z0) : z0; }
-    if (in1) { float2* q = buf + (g1 - offset); *q = APPLY ? cx_add_exact(*q, z1) : z1; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint64_t g = g0 + i;
+      if (g >= offset && g < offset + n) { float2* q = buf + (g - offset); *q = APPLY ? cx_add_exact(*q, z[i]) : z[i]; }
+    }
   }
 }
 static void awgn_launch(bool apply, float2* buf, size_t n, float scale, int twice, uint64_t seed, uint64_t stream,
                         uint64_t offset, cudaStream_t st) {
   if (n == 0) return;
-  const uint64_t pairs = ((offset + n + 1) >> 1) - (offset >> 1);
-  const int vec_ok = ((offset & 1) == 0) && ((uintptr_t)buf % 16) == 0;
-  const unsigned g = cdiv(pairs, 256);
+  const uint64_t quads = ((offset + n + 3) >> 2) - (offset >> 2);
+  const int vec_ok = ((offset & 3) == 0) && ((uintptr_t)buf % 32) == 0;
+  const unsigned g = cdiv(quads, 256);
   const PhiloxKeys keys = make_philox_keys(seed);
   if (apply) awgn_kernel<true><<<g, 256, 0, st>>>(buf, n, scale, twice, keys, stream, offset, vec_ok);
   else awgn_kernel<false><<<g, 256, 0, st>>>(buf, n, scale, twice, keys, stream, offset, vec_ok);
