@@ -210,4 +210,11 @@ __device__ __forceinline__ void st_stream_256(void* p, float4 a, float4 b) {
                : "memory");
 }
 
+// 256-bit streaming load (LDG.256); p must be 32-byte aligned
+__device__ __forceinline__ void ld_stream_256(const void* p, float4& a, float4& b) {
+  asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+
 }  // namespace ae

@@ -37,6 +37,17 @@ template <> struct VecIO<2> {
   }
 };
 
+template <> struct VecIO<4> {   // 256-bit accesses (sm_100 LDG.256 / STG.256), 32-byte aligned
+  static __device__ __forceinline__ void load(float2 (&d)[4], const float2* p) {
+    float4 a, b;
+    ld_stream_256(p, a, b);
+    d[0] = make_float2(a.x, a.y); d[1] = make_float2(a.z, a.w); d[2] = make_float2(b.x, b.y); d[3] = make_float2(b.z, b.w);
+  }
+  static __device__ __forceinline__ void store(float2* p, const float2 (&d)[4]) {
+    st_stream_256(p, make_float4(d[0].x, d[0].y, d[1].x, d[1].y), make_float4(d[2].x, d[2].y, d[3].x, d[3].y));
+  }
+};
+
 template <int W>
 __device__ __forceinline__ void tape_apply(float2 (&x)[W], const TapeEntry& e, size_t idx) {
   float2 o[W];
@@ -68,11 +79,12 @@ __device__ __forceinline__ void tape_apply(float2 (&x)[W], const TapeEntry& e, s
 }
 
 constexpr int kVecThreads = 256;
-constexpr int kVecUnroll = 4;
+__host__ __device__ constexpr int vec_unroll(int w) { return w == 4 ? 2 : 4; }   // 64 bytes per operand in flight per thread
 
 // no mirror in the tape: W consecutive samples per pack, kVecUnroll packs per thread
 template <int W>
 __global__ void __launch_bounds__(kVecThreads) vecops_kernel(float2* __restrict__ v, size_t n, const __grid_constant__ TapeParams p) {
+  constexpr int kVecUnroll = vec_unroll(W);
   const size_t packs = n / W;
   const size_t base = (size_t)blockIdx.x * (kVecThreads * kVecUnroll) + threadIdx.x;
   float2 x[kVecUnroll][W];
@@ -97,9 +109,9 @@ __global__ void __launch_bounds__(kVecThreads) vecops_kernel(float2* __restrict_
     const size_t i = base + (size_t)u * kVecThreads;
     if (i < packs) VecIO<W>::store(v + i * W, x[u]);
   }
-  if (W == 2 && (n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail element
+  if (W > 1 && blockIdx.x == 0 && threadIdx.x < n % W) {  // tail elements that do not fill a pack
     float2 t[1];
-    const size_t i = n - 1;
+    const size_t i = packs * W + threadIdx.x;
     t[0] = p.load_self ? v[i] : make_float2(0.0f, 0.0f);
     for (int k = 0; k < p.n_ops; ++k) tape_apply<1>(t, p.e[k], i);
     v[i] = t[0];
@@ -144,18 +156,25 @@ __global__ void __launch_bounds__(kVecThreads) vecops_mirror_kernel(float2* __re
 
 void launch_vecops(float2* v, size_t n, const TapeParams& p, bool has_mirror, int, cudaStream_t st) {
   if (n == 0) return;
-  bool aligned = ((uintptr_t)v % 16) == 0;
+  bool aligned = ((uintptr_t)v % 16) == 0, aligned32 = ((uintptr_t)v % 32) == 0;
   for (int k = 0; k < p.n_ops; ++k)
-    if (p.e[k].operand && ((uintptr_t)p.e[k].operand % 16) != 0) aligned = false;
+    if (p.e[k].operand) {
+      if (((uintptr_t)p.e[k].operand % 16) != 0) aligned = false;
+      if (((uintptr_t)p.e[k].operand % 32) != 0) aligned32 = false;
+    }
   if (!has_mirror) {
-    if (aligned && n >= 2) {
-      vecops_kernel<2><<<cdiv(n / 2, kVecThreads * kVecUnroll), kVecThreads, 0, st>>>(v, n, p);
+    if (aligned32 && n >= 4) {
+      vecops_kernel<4><<<cdiv(n / 4, kVecThreads * vec_unroll(4)), kVecThreads, 0, st>>>(v, n, p);
+    } else if (aligned && n >= 2) {
+      vecops_kernel<2><<<cdiv(n / 2, kVecThreads * vec_unroll(2)), kVecThreads, 0, st>>>(v, n, p);
     } else {
-      vecops_kernel<1><<<cdiv(n, kVecThreads * kVecUnroll), kVecThreads, 0, st>>>(v, n, p);
+      vecops_kernel<1><<<cdiv(n, kVecThreads * vec_unroll(1)), kVecThreads, 0, st>>>(v, n, p);
     }
   } else {
     const size_t mid = n / 2;
-    if (aligned && (mid % 2) == 0 && mid >= 2) {
+    if (aligned32 && (mid % 4) == 0 && mid >= 4) {
+      vecops_mirror_kernel<4><<<cdiv(mid / 4, kVecThreads), kVecThreads, 0, st>>>(v, n, p);
+    } else if (aligned && (mid % 2) == 0 && mid >= 2) {
       vecops_mirror_kernel<2><<<cdiv(mid / 2, kVecThreads), kVecThreads, 0, st>>>(v, n, p);
     } else {
       vecops_mirror_kernel<1><<<cdiv(mid ? mid : 1, kVecThreads), kVecThreads, 0, st>>>(v, n, p);
