@@ -337,8 +337,13 @@ __global__ void __launch_bounds__(256) demod_kernel(const __grid_constant__ ModT
   const size_t s0 = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
   if (s0 >= n) return;
   if (vec_ok && s0 + 4 <= n) {
-    const float4 a = __ldcs(reinterpret_cast<const float4*>(sym + s0));
-    const float4 b = __ldcs(reinterpret_cast<const float4*>(sym + s0) + 1);
+    float4 a, b;
+    if (vec_ok == 2) {
+      ld_stream_256(sym + s0, a, b);                       // four symbols in one 256-bit load
+    } else {
+      a = __ldcs(reinterpret_cast<const float4*>(sym + s0));
+      b = __ldcs(reinterpret_cast<const float4*>(sym + s0) + 1);
+    }
     uint8_t o[4 * BPS];
     demod_emit<M>(make_float2(a.x, a.y), tab, compat, o, generic);
     demod_emit<M>(make_float2(a.z, a.w), tab, compat, o + BPS, generic);
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(256) demod_kernel(const __grid_constant__ ModT
 }
 void launch_demod(const ModTable& tab, const float2* sym, size_t n, uint8_t* bits, int compat, cudaStream_t st) {
   if (n == 0) return;
-  const int vec_ok = ((uintptr_t)sym % 16) == 0 && ((uintptr_t)bits % 8) == 0;
+  const int vec_ok = (((uintptr_t)sym % 16) == 0 && ((uintptr_t)bits % 8) == 0) ? (((uintptr_t)sym % 32) == 0 ? 2 : 1) : 0;   // 2: 256-bit loads
   const unsigned g = cdiv(cdiv(n, 4), 256);
   if (tab.len == 2) demod_kernel<2><<<g, 256, 0, st>>>(tab, sym, n, bits, compat, vec_ok);
   else demod_kernel<4><<<g, 256, 0, st>>>(tab, sym, n, bits, compat, vec_ok);
@@ -383,7 +388,8 @@ __global__ void __launch_bounds__(256) awgn_kernel(float2* __restrict__ buf, siz
     float4* q = reinterpret_cast<float4*>(buf + (g0 - offset));
     float4 a = make_float4(z[0].x, z[0].y, z[1].x, z[1].y), b = make_float4(z[2].x, z[2].y, z[3].x, z[3].y);
     if (APPLY) {
-      const float4 s0 = __ldcs(q), s1 = __ldcs(q + 1);
+      float4 s0, s1;
+      ld_stream_256(q, s0, s1);
       a = make_float4(__fadd_rn(s0.x, a.x), __fadd_rn(s0.y, a.y), __fadd_rn(s0.z, a.z), __fadd_rn(s0.w, a.w));
       b = make_float4(__fadd_rn(s1.x, b.x), __fadd_rn(s1.y, b.y), __fadd_rn(s1.z, b.z), __fadd_rn(s1.w, b.w));
     }
@@ -643,15 +649,23 @@ __global__ void __launch_bounds__(kMseqThreads) mseq_kernel(uint64_t state, uint
   mseq_fill_bits(state, poly_low, deg, len, tab, s_bits);
   __syncthreads();
   const size_t block_start = (size_t)blockIdx.x * kMseqThreads * kMseqBitsPerThread;
-  const bool vec_ok = ((uintptr_t)out % 16) == 0;
-  for (int q = threadIdx.x; q < kMseqThreads * kMseqBitsPerThread / 16; q += kMseqThreads) {
-    const size_t n = block_start + 16 * (size_t)q;
+  const bool vec32 = ((uintptr_t)out % 32) == 0;
+  for (int q2 = threadIdx.x; q2 < kMseqThreads * kMseqBitsPerThread / 32; q2 += kMseqThreads) {   // 32 bits -> 32 bytes per step
+    const size_t n = block_start + 32 * (size_t)q2;
     if (n >= len) break;
-    const uint32_t b16 = s_bits[(q % (kMseqBitsPerThread / 16)) * kMseqPitch + q / (kMseqBitsPerThread / 16)];
-    if (n + 16 <= len && vec_ok) {
-      __stcs(reinterpret_cast<uint4*>(out + n), make_uint4(spread4(b16), spread4(b16 >> 4), spread4(b16 >> 8), spread4(b16 >> 12)));
+    uint32_t b[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = 2 * q2 + h;
+      b[h] = s_bits[(q % (kMseqBitsPerThread / 16)) * kMseqPitch + q / (kMseqBitsPerThread / 16)];
+    }
+    if (n + 32 <= len && vec32) {
+      const uint4 lo = make_uint4(spread4(b[0]), spread4(b[0] >> 4), spread4(b[0] >> 8), spread4(b[0] >> 12));
+      const uint4 hi = make_uint4(spread4(b[1]), spread4(b[1] >> 4), spread4(b[1] >> 8), spread4(b[1] >> 12));
+      st_stream_256(out + n, make_float4(__uint_as_float(lo.x), __uint_as_float(lo.y), __uint_as_float(lo.z), __uint_as_float(lo.w)),
+                    make_float4(__uint_as_float(hi.x), __uint_as_float(hi.y), __uint_as_float(hi.z), __uint_as_float(hi.w)));
     } else {
-      for (int i = 0; i < 16 && n + i < len; ++i) out[n + i] = (uint8_t)((b16 >> i) & 1u);
+      for (int i = 0; i < 32 && n + i < len; ++i) out[n + i] = (uint8_t)((b[i >> 4] >> (i & 15)) & 1u);
     }
   }
 }
