@@ -96,3 +96,23 @@ def test_util_db_matches_the_reference_tests():
     assert DB(30.0).ratio() == 1000.0 and DB(0.0).ratio() == 1.0
     assert abs(DB.from_ratio(100.0).db() - 20.0) < 1e-6 and abs(DB.from_ratio(0.1).db() + 10.0) < 1e-6
     assert DB.from_ratio(0.0).db() == float("-inf")
+
+
+def test_committed_bench_line_carries_the_contract_keys():
+    """The latest bench line under profiles/ (written by `python bench.py` on a B200) has every key the
+    bench contract names; guards against a key being dropped by a later edit of bench.py."""
+    import glob
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = sorted(glob.glob(os.path.join(root, "profiles", "r1_bench_v[0-9]*.json")), key=lambda p: int(re.findall(r"_v(\d+)", p)[0]))
+    d = json.load(open(lines[-1]))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+    assert "workload" in d["config"] and d["gpu_launches"] > 0 and d["n_gpus"] == 1
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
