@@ -431,9 +431,13 @@ static const uint32_t* ofdm_column_table(int T, cudaStream_t st) {
       if (x[n]) h[(size_t)i * T + n / 32] |= 1u << (n % 32);
   }
   uint32_t* d = nullptr;
-  cudaMalloc((void**)&d, h.size() * sizeof(uint32_t));
-  cudaMemcpyAsync(d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
-  cudaStreamSynchronize(st);
+  // on failure the CUDA error stays pending and is reported by the caller's launch check
+  if (cudaMalloc((void**)&d, h.size() * sizeof(uint32_t)) != cudaSuccess) return nullptr;
+  if (cudaMemcpyAsync(d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess) {
+    cudaFree(d);
+    return nullptr;
+  }
   cache[key] = d;
   return d;
 }
@@ -445,6 +449,7 @@ static void launch_ofdm_n(size_t frames, uint64_t first_frame, float noise_scale
   const size_t smem = LC::SMEM_PER_FRAME * LC::F;
   const size_t want = (frames + LC::F - 1) / LC::F;
   const uint32_t* zj = ofdm_column_table(FftCfg<N>::T, st);
+  if (!zj) return;
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 1, dev = 0, sms = 148;
