@@ -519,6 +519,17 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             cpu = {"value": gs, "unit": "Gsamples/s", "cores": threads, "kind": "port",
                    "sample": "%d frames x %d samples, %d host threads, %.1f s; C++ restatement of aether_primitives (not rustfft)" % (cf, FFT_LEN, threads, ms / 1e3),
                    "single_thread_value": gs1}
+            try:  # second, independent CPU yard-stick for the FFT alone: scipy's pocketfft, complex64
+                import scipy.fft as sfft
+
+                xf = (np.random.default_rng(2).standard_normal((1 << 14, FFT_LEN)) + 0j).astype(np.complex64)
+                sfft.fft(xf, axis=1, workers=threads)
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    sfft.fft(xf, axis=1, workers=threads)
+                cpu["scipy_pocketfft_fft1024_Gsamples/s"] = 5 * xf.size / (time.perf_counter() - t0) / 1e9
+            except Exception:
+                pass
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
