@@ -300,4 +300,17 @@ struct DB {
   double ratio() const { return std::pow(10.0, value / 10.0); }
 };
 
+/// assert_evm!(actual, ref[, evm_limit_db]) (src/lib.rs:26-49) on host data: per element
+/// |act - re| > |re| * (10^(dB/10) as f32) panics (here: throws Panic with the macro's message text).
+inline void assert_evm(const std::vector<cf32>& actual, const std::vector<cf32>& ref, double evm_limit_db = -80.0) {
+  if (actual.size() != ref.size()) throw Panic(AE_ELEN, "Input slices/vectors must be same length");
+  if (!(evm_limit_db < 0.0)) throw Panic(AE_EARG, "The EVM threshold must be negative");
+  const float factor = (float)std::pow(10.0, evm_limit_db / 10.0);
+  for (size_t i = 0; i < actual.size(); ++i) {
+    const float evm = std::abs(actual[i] - ref[i]);
+    const float limit = std::abs(ref[i]) * factor;
+    if (evm > limit) throw Panic(AE_EARG, "EVM limit exceeded for element " + std::to_string(i));
+  }
+}
+
 }  // namespace aether

@@ -116,3 +116,31 @@ def test_committed_bench_line_carries_the_contract_keys():
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
     assert "workload" in d["config"] and d["gpu_launches"] > 0 and d["n_gpus"] == 1
     assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+
+
+def test_util_assert_evm_agrees_with_the_oracle_restatement():
+    """assert_evm! (src/lib.rs:26-49; its tests :87-118): same pass/fail and same first failing element as the oracle."""
+    import numpy as np
+
+    from aether_primitives_b200.util import assert_evm
+    from tests import oracle as o
+
+    ones = np.full(100, 1 + 1j, np.complex64)
+    assert_evm(ones, ones)                                              # evm_passes
+    assert_evm(ones, ones * np.float32(1 + 1e-9), -80.0)
+    with pytest.raises(AssertionError, match="EVM limit exceeded"):     # evm_fails
+        assert_evm(ones, ones * np.float32(1.1), -80.0)
+    with pytest.raises(AssertionError, match="same length"):
+        assert_evm(ones, ones[:-1])
+    with pytest.raises(AssertionError, match="must be negative"):
+        assert_evm(ones, ones, 3.0)
+    rng = np.random.default_rng(3)
+    for db in (-80.0, -40.0, -20.0, -6.0):
+        r = (rng.standard_normal(500) + 1j * rng.standard_normal(500)).astype(np.complex64)
+        a = (r * np.float32(1 + 10 ** (db / 10)) + np.float32(1e-7)).astype(np.complex64)   # straddles the limit
+        rc, bad = o.assert_evm(a, r, db)
+        try:
+            assert_evm(a, r, db)
+            assert rc == o.OK
+        except AssertionError as ex:
+            assert rc == o.EVM_EXCEEDED and ("for element %d." % bad) in str(ex)
