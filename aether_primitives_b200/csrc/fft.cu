@@ -46,6 +46,7 @@ fft_pow2_kernel(const float2* __restrict__ in, float2* __restrict__ out, const f
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)LC::F * (C::SMEM_ELEMS + (STAGED ? N : 0))) + f;
   const size_t stride = (size_t)gridDim.x * LC::F;
   size_t frame = (size_t)blockIdx.x * LC::F + f;
+  const bool wide = (((uintptr_t)in | (uintptr_t)out) % 32) == 0;   // 256-bit accesses allowed (used when T == 1)
   if (STAGED) {
     if (t == 0) {
       mbar_init(bar, 1);
@@ -69,8 +70,20 @@ fft_pow2_kernel(const float2* __restrict__ in, float2* __restrict__ out, const f
       for (int m = 0; m < 16; ++m) x[0][m] = xin[t + m * C::T];
     } else {
       const float2* src = in + frame * N;
+      if (C::T == 1 && wide) {
+        // N = 16: the thread owns the whole 128-byte frame - four 256-bit loads instead of sixteen 64-bit
+        // loads that each touch 32 different lines per warp
 #pragma unroll
-      for (int m = 0; m < 16; ++m) x[0][m] = ld_stream(src + t + m * C::T);
+        for (int j = 0; j < 4; ++j) {
+          float4 a, b;
+          ld_stream_256(src + 4 * j, a, b);
+          x[0][4 * j] = make_float2(a.x, a.y); x[0][4 * j + 1] = make_float2(a.z, a.w);
+          x[0][4 * j + 2] = make_float2(b.x, b.y); x[0][4 * j + 3] = make_float2(b.z, b.w);
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) x[0][m] = ld_stream(src + t + m * C::T);
+      }
     }
     auto prefetch = [&]() {
       if (STAGED && t == 0 && frame + stride < frames) {
@@ -90,8 +103,15 @@ fft_pow2_kernel(const float2* __restrict__ in, float2* __restrict__ out, const f
 #pragma unroll
       for (int m = 0; m < 16; ++m) x[0][m] = cx_scale_exact(x[0][m], scale);
     }
+    if (C::T == 1 && wide) {
 #pragma unroll
-    for (int m = 0; m < 16; ++m) st_stream(dst + t + m * C::T, x[0][m]);
+      for (int j = 0; j < 4; ++j)
+        st_stream_256(dst + 4 * j, make_float4(x[0][4 * j].x, x[0][4 * j].y, x[0][4 * j + 1].x, x[0][4 * j + 1].y),
+                      make_float4(x[0][4 * j + 2].x, x[0][4 * j + 2].y, x[0][4 * j + 3].x, x[0][4 * j + 3].y));
+    } else {
+#pragma unroll
+      for (int m = 0; m < 16; ++m) st_stream(dst + t + m * C::T, x[0][m]);
+    }
     // the next frame's first pass stores into the same shared frame: everyone must be past its reads
     if (C::NP > 1) frame_sync<C::T>(f);
   }
