@@ -6,14 +6,14 @@ NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt
 CSRC      := aether_primitives_b200/csrc
 LIBDIR    := aether_primitives_b200/lib
 OBJDIR    := build/obj
-SRCS      := api elementwise fft fir chain spectral
+SRCS      := api elementwise fft fir chain chain_x2 spectral
 OBJS      := $(addprefix $(OBJDIR)/,$(addsuffix .o,$(SRCS)))
 LIB       := $(LIBDIR)/libaether_b200.so
 ORACLE    := oracle/liboracle.so
 
 all: $(LIB) $(ORACLE)
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(CSRC)/internal.h include/aether_b200.h
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/aether_b200.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
 

@@ -1316,6 +1316,8 @@ struct ae_chain {
   float x, s;
   bool fused;
   float2 *d_tw, *d_window, *d_taps;
+  bool x2;                                // K14b applies (N = 1024, <= 64 taps)
+  float2 *d_x2tw, *d_taps_hi, *d_taps_lo;
   ae_fft* fft;
   ae_fir* fir;
   ae_mod* qpsk;
@@ -1344,7 +1346,10 @@ ae_status ae_chain_create(size_t fft_len, const ae_cf32* taps_host, size_t ntaps
   if (st == AE_OK) st = ae_mod_qpsk(&ch->qpsk);
   if (st != AE_OK) { ae_chain_destroy(ch); return st; }
   if (ch->fused) {
-    TRY(get_thread_twiddles(c, fft_len, &ch->d_tw));
+    // every failure below goes through ae_chain_destroy (nothing leaks)
+    auto fail_out = [&](ae_status e) { ae_chain_destroy(ch); return e; };
+    st = get_thread_twiddles(c, fft_len, &ch->d_tw);
+    if (st != AE_OK) return fail_out(st);
     // window[m] = s * sum_k h[k] exp(-sgn 2 pi i m k / N), sgn = exponent sign of Cfft::fwd
     const double sgn = (compat == AE_COMPAT_REFERENCE) ? +1.0 : -1.0;
     std::vector<float2> w(fft_len), h(ntaps);
@@ -1359,12 +1364,26 @@ ae_status ae_chain_create(size_t fft_len, const ae_cf32* taps_host, size_t ntaps
       w[m] = make_float2((float)(ar * (double)ch->s), (float)(ai * (double)ch->s));
     }
     for (size_t k = 0; k < ntaps; ++k) h[k] = make_float2(taps_host[k].re, taps_host[k].im);
-    void* p;
-    TRY(dev_alloc(c, fft_len * sizeof(float2), &p)); ch->d_window = (float2*)p;
-    TRY(dev_alloc(c, ntaps * sizeof(float2), &p)); ch->d_taps = (float2*)p;
-    CK(cudaMemcpyAsync(ch->d_window, w.data(), fft_len * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(ch->d_taps, h.data(), ntaps * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    auto upload = [&](const std::vector<float2>& v, float2** dst) -> ae_status {
+      void* p = nullptr;
+      TRY(dev_alloc(c, v.size() * sizeof(float2), &p));
+      *dst = (float2*)p;
+      CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+      return AE_OK;
+    };
+    st = upload(w, &ch->d_window);
+    if (st == AE_OK) st = upload(h, &ch->d_taps);
+    static const char* force_v1 = getenv("AE_CHAIN_V1");   // developer switch: K14 (chain.cu) instead of K14b
+    ch->x2 = chain_x2_supported(fft_len, ntaps) && !force_v1;
+    if (st == AE_OK && ch->x2) {
+      std::vector<float2> tw, hi, lo;
+      chain_x2_tables(fft_len, h.data(), ntaps, tw, hi, lo);
+      st = upload(tw, &ch->d_x2tw);
+      if (st == AE_OK) st = upload(hi, &ch->d_taps_hi);
+      if (st == AE_OK) st = upload(lo, &ch->d_taps_lo);
+    }
+    if (st == AE_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = fail(AE_ECUDA, "chain table upload failed");
+    if (st != AE_OK) return fail_out(st);
   }
   *out = ch;
   return AE_OK;
@@ -1374,10 +1393,22 @@ ae_status ae_chain_destroy(ae_chain* ch) {
   cudaSetDevice(ch->c->dev);
   ae_fft_destroy(ch->fft); ae_fir_destroy(ch->fir); ae_mod_destroy(ch->qpsk);
   dev_free(ch->c, ch->d_window); dev_free(ch->c, ch->d_taps);
+  dev_free(ch->c, ch->d_x2tw); dev_free(ch->c, ch->d_taps_hi); dev_free(ch->c, ch->d_taps_lo);
   for (int i = 0; i < 3; ++i) { if (ch->d_in[i]) cudaFree(ch->d_in[i]); if (ch->d_out[i]) cudaFree(ch->d_out[i]); }
   delete ch;
   return AE_OK;
 }
+
+}  // extern "C"
+// one launch of the fused chain: K14b when it applies and the bit buffer is 4-byte aligned, K14 otherwise
+static void chain_launch(ae_chain* ch, const float2* x, uint8_t* bits, size_t frames, cudaStream_t st) {
+  const bool inverse = (ch->compat == AE_COMPAT_REFERENCE);
+  if (ch->x2 && ((uintptr_t)bits % 4) == 0)
+    launch_chain_x2(x, bits, frames, ch->d_window, ch->d_x2tw, ch->d_taps_hi, ch->d_taps_lo, ch->ntaps, inverse, ch->s, ch->compat, st);
+  else
+    launch_chain_fused(x, bits, ch->n, frames, ch->d_window, ch->d_taps, ch->ntaps, ch->d_tw, inverse, ch->s, ch->compat, st);
+}
+extern "C" {
 
 ae_status ae_chain_exec_unfused(ae_chain* ch, ae_vec* in, ae_bits* bits_out, ae_vec* symbols_out) {
   if (!ch || !in || !bits_out) return fail(AE_EARG, "null");
@@ -1407,9 +1438,7 @@ ae_status ae_chain_exec(ae_chain* ch, ae_vec* in, ae_bits* bits_out) {
   TRY(before_read(in));
   TRY(bits_reserve(bits_out, 2 * in->len));
   bits_out->len = 2 * in->len;
-  const bool inverse = (ch->compat == AE_COMPAT_REFERENCE);
-  launch_chain_fused(vptr(in), bptr(bits_out), ch->n, frames, ch->d_window, ch->d_taps, ch->ntaps, ch->d_tw, inverse, ch->s,
-                     ch->compat, c->stream);
+  chain_launch(ch, vptr(in), bptr(bits_out), frames, c->stream);
   if (frames) CKL(1);
   return AE_OK;
 }
@@ -1429,7 +1458,6 @@ ae_status ae_chain_exec_host(ae_chain* ch, const ae_cf32* host_in, size_t n_samp
       CK(cudaMalloc((void**)&ch->d_out[i], ch->chunk_frames * ch->n * 2));
     }
   }
-  const bool inverse = (ch->compat == AE_COMPAT_REFERENCE);
   // order the pipeline after work already queued on the context stream
   cudaEvent_t ev;
   CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1441,8 +1469,7 @@ ae_status ae_chain_exec_host(ae_chain* ch, const ae_cf32* host_in, size_t n_samp
     const size_t fc = std::min(ch->chunk_frames, frames - done);
     cudaStream_t st = c->pipe[slot];
     CK(cudaMemcpyAsync(ch->d_in[slot], host_in + done * ch->n, fc * ch->n * sizeof(float2), cudaMemcpyHostToDevice, st));
-    launch_chain_fused(ch->d_in[slot], ch->d_out[slot], ch->n, fc, ch->d_window, ch->d_taps, ch->ntaps, ch->d_tw, inverse,
-                       ch->s, ch->compat, st);
+    chain_launch(ch, ch->d_in[slot], ch->d_out[slot], fc, st);
     CKL(1);
     CK(cudaMemcpyAsync(host_bits + 2 * done * ch->n, ch->d_out[slot], fc * ch->n * 2, cudaMemcpyDeviceToHost, st));
     done += fc;
@@ -1557,8 +1584,7 @@ ae_status ae_pipe_send(ae_pipe* p, const ae_cf32* host_in, uint8_t* host_bits) {
   CK(cudaEventRecord(s.ev[0], s.st));
   CK(cudaMemcpyAsync(s.d_in, host_in, ns * sizeof(float2), cudaMemcpyHostToDevice, s.st));
   CK(cudaEventRecord(s.ev[1], s.st));
-  launch_chain_fused(s.d_in, s.d_out, ch->n, p->block_frames, ch->d_window, ch->d_taps, ch->ntaps, ch->d_tw,
-                     ch->compat == AE_COMPAT_REFERENCE, ch->s, ch->compat, s.st);
+  chain_launch(ch, s.d_in, s.d_out, p->block_frames, s.st);
   CKL(1);
   CK(cudaEventRecord(s.ev[2], s.st));
   CK(cudaMemcpyAsync(host_bits, s.d_out, ns * 2, cudaMemcpyDeviceToHost, s.st));

@@ -92,6 +92,13 @@ bool chain_fused_supported(size_t nfft, size_t ntaps);
 void launch_chain_fused(const float2* x, uint8_t* bits, size_t nfft, size_t frames, const float2* window,
                         const float2* taps, size_t ntaps, const float2* tw, bool inverse, float scale, int compat,
                         cudaStream_t st);
+// K14b (chain_x2.cuh): N = 1024, <= 64 taps; packed FP32 butterflies, warp per frame, tensor-core fix-up.
+// tw = chain_x2_twiddles() rows, taps_hi/lo = chain_x2_split_taps(); bits must be 4-byte aligned.
+bool chain_x2_supported(size_t nfft, size_t ntaps);
+void chain_x2_tables(size_t nfft, const float2* taps, size_t ntaps, std::vector<float2>& tw, std::vector<float2>& hi,
+                     std::vector<float2>& lo);
+void launch_chain_x2(const float2* x, uint8_t* bits, size_t frames, const float2* window, const float2* tw, const float2* taps_hi,
+                     const float2* taps_lo, size_t ntaps, bool inverse, float scale, int compat, cudaStream_t st);
 bool ofdm_supported(size_t nfft);
 void launch_ofdm_chain(size_t nfft, size_t frames, uint64_t first_frame, float noise_scale, int twice, uint64_t seed,
                        const float2* tw, int compat, uint8_t* tx_bits, uint8_t* rx_bits, ae_stats* stats,
