@@ -138,6 +138,13 @@ _SIGS = {
     "ae_stats_read": (None, [_P, C.POINTER(Stats)]),
     "ae_count_bit_errors": (None, [_P, _P, _P]),
     "ae_evm_accumulate": (None, [_P, _P, _P]),
+    "ae_comm_unique_id": (None, [_P]),
+    "ae_comm_init_rank": (None, [_P, _I, _I, C.POINTER(_P)]),
+    "ae_comm_init_all": (None, [_I, C.POINTER(_P)]),
+    "ae_comm_destroy": (None, [_P]),
+    "ae_comm_info": (None, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "ae_stats_allreduce": (None, [_P, _P]),
+    "ae_stats_allreduce_all": (None, [C.POINTER(_P), C.POINTER(_P), _I]),
     "ae_modem_fused": (None, [_P, _P, _P, _P, _P, _I]),
     "ae_chain_create": (None, [_SZ, _P, _SZ, _I, _F, _I, C.POINTER(_P)]),
     "ae_chain_destroy": (None, [_P]),

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <dlfcn.h>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -198,23 +199,31 @@ ae_status flush_vec(ae_vec* v) {
   return AE_OK;
 }
 
+// Two allocations alias when their device address ranges overlap: an Alloc is unique for library
+// memory, but ae_vec_wrap / ae_bits_wrap can wrap the same foreign pointer more than once.
+bool same_mem(const Alloc* x, const Alloc* y) {
+  if (x == y) return true;
+  if (!x || !y || (x->owned && y->owned)) return false;
+  const char *xb = (const char*)x->p, *yb = (const char*)y->p;
+  return xb < yb + y->bytes && yb < xb + x->bytes;
+}
 bool tape_reads(const ae_vec* p, const Alloc* a) {
   for (const TapeRec& r : p->tape)
-    if (r.oa == a) return true;
+    if (r.oa && same_mem(r.oa, a)) return true;
   return false;
 }
 // make the memory behind `v` current (its own tape and any alias of the same allocation)
 ae_status before_read(ae_vec* v) {
   std::vector<ae_vec*> snap = v->c->pending;
   for (ae_vec* p : snap)
-    if (p->a == v->a) TRY(flush_vec(p));
+    if (same_mem(p->a, v->a)) TRY(flush_vec(p));
   return AE_OK;
 }
 // additionally run every tape that still wants to read the old contents of `v`
 ae_status before_write(ae_vec* v) {
   std::vector<ae_vec*> snap = v->c->pending;
   for (ae_vec* p : snap)
-    if (p->a == v->a || tape_reads(p, v->a)) TRY(flush_vec(p));
+    if (same_mem(p->a, v->a) || tape_reads(p, v->a)) TRY(flush_vec(p));
   return AE_OK;
 }
 
@@ -229,9 +238,9 @@ ae_status record(ae_vec* v, int op, ae_vec* other, float s) {
   std::vector<ae_vec*> snap = v->c->pending;
   for (ae_vec* p : snap) {
     if (p == v) continue;
-    if (p->a == v->a || tape_reads(p, v->a) || (binary && p->a == other->a)) TRY(flush_vec(p));
+    if (same_mem(p->a, v->a) || tape_reads(p, v->a) || (binary && same_mem(p->a, other->a))) TRY(flush_vec(p));
   }
-  if (binary && other->a == v->a) TRY(flush_vec(v));  // operand aliases self: snapshot current values
+  if (binary && same_mem(other->a, v->a)) TRY(flush_vec(v));  // operand aliases self: snapshot current values
   if ((int)v->tape.size() >= kMaxTape) TRY(flush_vec(v));
   if (op == OP_ZERO || op == OP_CLONE) {  // everything recorded before is dead
     for (TapeRec& r : v->tape) alloc_unref(v->c, r.oa);
@@ -310,19 +319,29 @@ ae_status ae_init(int device) {
   if (!g_ctx[device]) {
     Ctx* c = new Ctx;
     c->dev = device;
-    CK(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
-    c->stream = c->own;
-    for (int i = 0; i < 3; ++i) CK(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    c->sm_count = prop.multiProcessorCount;
-    if (prop.major != 10) {
+    // a failure half-way releases what was created (the mutex guard unlocks on every return)
+    auto build = [&]() -> ae_status {
+      CK(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
+      c->stream = c->own;
+      for (int i = 0; i < 3; ++i) CK(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
+      cudaDeviceProp prop;
+      CK(cudaGetDeviceProperties(&prop, device));
+      c->sm_count = prop.multiProcessorCount;
+      if (prop.major != 10)
+        return fail(AE_ECUDA, "aether_b200 kernels are built for sm_100a (B200) only; found compute capability " +
+                                  std::to_string(prop.major) + "." + std::to_string(prop.minor));
+      CK(cudaMalloc((void**)&c->d_err, sizeof(int)));
+      CK(cudaMemset(c->d_err, 0, sizeof(int)));
+      return AE_OK;
+    };
+    const ae_status st = build();
+    if (st != AE_OK) {
+      if (c->own) cudaStreamDestroy(c->own);
+      for (int i = 0; i < 3; ++i) if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
+      if (c->d_err) cudaFree(c->d_err);
       delete c;
-      return fail(AE_ECUDA, "aether_b200 kernels are built for sm_100a (B200) only; found compute capability " +
-                                std::to_string(prop.major) + "." + std::to_string(prop.minor));
+      return st;
     }
-    CK(cudaMalloc((void**)&c->d_err, sizeof(int)));
-    CK(cudaMemset(c->d_err, 0, sizeof(int)));
     // keep freed blocks in the stream-ordered pool instead of returning them to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -356,9 +375,11 @@ void* ae_get_stream(void) {
   return (void*)c->stream;
 }
 
-ae_status ae_sync(void) {
-  Ctx* c;
-  TRY(get_ctx(&c));
+}  // extern "C"
+// synchronise ONE context (the handle's, which need not be the calling thread's current device) and
+// report its deferred device-side error flag
+static ae_status sync_ctx(Ctx* c) {
+  cudaSetDevice(c->dev);
   int flag = 0;
   CK(cudaMemcpyAsync(&flag, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -368,6 +389,12 @@ ae_status ae_sync(void) {
     return fail(AE_ECUDA, "device-side error flag set");
   }
   return AE_OK;
+}
+extern "C" {
+ae_status ae_sync(void) {
+  Ctx* c;
+  TRY(get_ctx(&c));
+  return sync_ctx(c);
 }
 const char* ae_last_error_string(void) { return t_err.c_str(); }
 ae_status ae_sm_count(int* n) {
@@ -431,13 +458,19 @@ ae_status ae_vec_free(ae_vec* v) {
   if (!v || v->plan_owned) return AE_OK;
   cudaSetDevice(v->c->dev);
   ae_status st = AE_OK;
-  if (v->a->refs > 1) st = flush_vec(v);  // someone else can still observe the memory
+  if (!v->a->owned) {
+    // borrowed memory (ae_vec_wrap): its owner observes it after the handle is gone, and may free it.
+    // Run the handle's own tape AND every pending tape that still reads this memory.
+    std::vector<ae_vec*> snap = v->c->pending;
+    for (ae_vec* p : snap)
+      if (p == v || same_mem(p->a, v->a) || tape_reads(p, v->a)) { ae_status s2 = flush_vec(p); if (st == AE_OK) st = s2; }
+  } else if (v->a->refs > 1) st = flush_vec(v);  // someone else can still observe the memory
   else {
     for (TapeRec& r : v->tape) alloc_unref(v->c, r.oa);
     v->tape.clear();
     drop_pending(v);
   }
-  // tapes that read this allocation keep it alive through their own reference
+  // tapes that read an owned allocation keep it alive through their own reference
   alloc_unref(v->c, v->a);
   delete v;
   return st;
@@ -480,7 +513,7 @@ ae_status ae_vec_download(ae_vec* v, ae_cf32* host, size_t n) {
   cudaSetDevice(v->c->dev);
   TRY(before_read(v));
   if (n) CK(cudaMemcpyAsync(host, vptr(v), n * sizeof(float2), cudaMemcpyDeviceToHost, v->c->stream));
-  return ae_sync();
+  return sync_ctx(v->c);
 }
 
 ae_status ae_vec_scale(ae_vec* v, float s) { return record(v, OP_SCALE, nullptr, s); }
@@ -582,7 +615,7 @@ ae_status ae_bits_download(ae_bits* b, uint8_t* host, size_t n) {
   if (n != b->len) return fail(AE_ELEN, "Vectors must have same length");
   cudaSetDevice(b->c->dev);
   if (n) CK(cudaMemcpyAsync(host, bptr(b), n, cudaMemcpyDeviceToHost, b->c->stream));
-  return ae_sync();
+  return sync_ctx(b->c);
 }
 
 }  // extern "C"
@@ -1245,6 +1278,167 @@ ae_status ae_stats_read(const ae_stats* d, ae_stats* host) {
   CK(cudaMemcpyAsync(host, d, sizeof(ae_stats), cudaMemcpyDeviceToHost, c->stream));
   return ae_sync();
 }
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// The one collective of the path: ae_stats summed over the GPUs with NCCL.  NCCL is bound at
+// run time (dlopen of the image's libnccl.so.2, or the copy torch already loaded), so the library has no
+// link-time dependency on it; the handful of declarations below are NCCL's stable C ABI.
+// -------------------------------------------------------------------------------------------------
+namespace {
+struct NcclId { char internal[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclId, int) = nullptr;
+  int (*CommInitAll)(NcclComm*, int, const int*) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+constexpr int kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values
+NcclApi& nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // torch's copy when it is already in the process
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { api.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+    bool all = true;
+    auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) { all = false; api.why = std::string("libnccl lacks ") + n; } return p; };
+    api.GetUniqueId = (int (*)(NcclId*))sym("ncclGetUniqueId");
+    api.CommInitRank = (int (*)(NcclComm*, int, NcclId, int))sym("ncclCommInitRank");
+    api.CommInitAll = (int (*)(NcclComm*, int, const int*))sym("ncclCommInitAll");
+    api.CommDestroy = (int (*)(NcclComm))sym("ncclCommDestroy");
+    api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclAllReduce");
+    api.GroupStart = (int (*)())sym("ncclGroupStart");
+    api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    api.ok = all;
+  });
+  return api;
+}
+ae_status nccl_fail(const NcclApi& n, int rc, const char* what) {
+  return fail(AE_ENCCL, std::string(what) + ": " + (n.GetErrorString ? n.GetErrorString(rc) : "NCCL error"));
+}
+#define NCK(call, what)                                  \
+  do {                                                   \
+    int r__ = (call);                                    \
+    if (r__ != 0) return nccl_fail(n, r__, what);        \
+  } while (0)
+}  // namespace
+
+struct ae_comm {
+  Ctx* c;
+  NcclComm comm;
+  int nranks, rank;
+};
+
+namespace {
+// both reductions of one ae_stats (two u64 counters, two f64 sums), to be called inside an NCCL group
+ae_status stats_allreduce_enqueue(NcclApi& n, ae_stats* d, ae_comm* cm) {
+  cudaSetDevice(cm->c->dev);
+  NCK(n.AllReduce(&d->bit_errors, &d->bit_errors, 2, kNcclUint64, kNcclSum, cm->comm, cm->c->stream), "ncclAllReduce(u64)");
+  NCK(n.AllReduce(&d->err_pow, &d->err_pow, 2, kNcclFloat64, kNcclSum, cm->comm, cm->c->stream), "ncclAllReduce(f64)");
+  return AE_OK;
+}
+}  // namespace
+
+extern "C" {
+
+ae_status ae_comm_unique_id(uint8_t id_out[AE_COMM_ID_BYTES]) {
+  if (!id_out) return fail(AE_EARG, "null");
+  NcclApi& n = nccl();
+  if (!n.ok) return fail(AE_ENCCL, n.why);
+  NcclId id;
+  NCK(n.GetUniqueId(&id), "ncclGetUniqueId");
+  static_assert(sizeof(NcclId) == AE_COMM_ID_BYTES, "NCCL unique id is 128 bytes");
+  std::memcpy(id_out, &id, sizeof(id));
+  return AE_OK;
+}
+ae_status ae_comm_init_rank(const uint8_t id_in[AE_COMM_ID_BYTES], int nranks, int rank, ae_comm** out) {
+  if (!id_in || !out) return fail(AE_EARG, "null");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(AE_EARG, "bad rank / nranks");
+  NcclApi& n = nccl();
+  if (!n.ok) return fail(AE_ENCCL, n.why);
+  Ctx* c;
+  TRY(get_ctx(&c));
+  NcclId id;
+  std::memcpy(&id, id_in, sizeof(id));
+  NcclComm comm = nullptr;
+  NCK(n.CommInitRank(&comm, nranks, id, rank), "ncclCommInitRank");
+  *out = new ae_comm{c, comm, nranks, rank};
+  return AE_OK;
+}
+ae_status ae_comm_init_all(int ndev, ae_comm** comms_out) {
+  if (!comms_out || ndev < 1) return fail(AE_EARG, "null / ndev < 1");
+  NcclApi& n = nccl();
+  if (!n.ok) return fail(AE_ENCCL, n.why);
+  const int keep = t_dev;
+  std::vector<Ctx*> ctx(ndev);
+  std::vector<int> devs(ndev);
+  for (int i = 0; i < ndev; ++i) {
+    ae_status st = ae_init(i);
+    if (st == AE_OK) st = get_ctx(&ctx[i]);
+    if (st != AE_OK) { if (keep >= 0) ae_init(keep); return st; }
+    devs[i] = i;
+  }
+  if (keep >= 0) ae_init(keep);
+  std::vector<NcclComm> comms(ndev, nullptr);
+  NCK(n.CommInitAll(comms.data(), ndev, devs.data()), "ncclCommInitAll");
+  for (int i = 0; i < ndev; ++i) comms_out[i] = new ae_comm{ctx[i], comms[i], ndev, i};
+  return AE_OK;
+}
+ae_status ae_comm_destroy(ae_comm* cm) {
+  if (!cm) return AE_OK;
+  NcclApi& n = nccl();
+  cudaSetDevice(cm->c->dev);
+  cudaStreamSynchronize(cm->c->stream);
+  int rc = n.ok ? n.CommDestroy(cm->comm) : 0;
+  delete cm;
+  if (rc != 0) return nccl_fail(n, rc, "ncclCommDestroy");
+  return AE_OK;
+}
+ae_status ae_comm_info(const ae_comm* cm, int* nranks, int* rank, int* device) {
+  if (!cm) return fail(AE_EARG, "null");
+  if (nranks) *nranks = cm->nranks;
+  if (rank) *rank = cm->rank;
+  if (device) *device = cm->c->dev;
+  return AE_OK;
+}
+ae_status ae_stats_allreduce(ae_stats* d, ae_comm* cm) {
+  if (!d || !cm) return fail(AE_EARG, "null");
+  NcclApi& n = nccl();
+  if (!n.ok) return fail(AE_ENCCL, n.why);
+  NCK(n.GroupStart(), "ncclGroupStart");
+  ae_status st = stats_allreduce_enqueue(n, d, cm);
+  const int rc = n.GroupEnd();
+  if (st != AE_OK) return st;
+  if (rc != 0) return nccl_fail(n, rc, "ncclGroupEnd");
+  return AE_OK;
+}
+ae_status ae_stats_allreduce_all(ae_stats** d, ae_comm** cm, int ndev) {
+  if (!d || !cm || ndev < 1) return fail(AE_EARG, "null / ndev < 1");
+  for (int i = 0; i < ndev; ++i)
+    if (!d[i] || !cm[i]) return fail(AE_EARG, "null");
+  NcclApi& n = nccl();
+  if (!n.ok) return fail(AE_ENCCL, n.why);
+  const int keep = t_dev;
+  NCK(n.GroupStart(), "ncclGroupStart");
+  ae_status st = AE_OK;
+  for (int i = 0; i < ndev && st == AE_OK; ++i) st = stats_allreduce_enqueue(n, d[i], cm[i]);
+  const int rc = n.GroupEnd();
+  if (keep >= 0) cudaSetDevice(g_ctx[keep]->dev);
+  if (st != AE_OK) return st;
+  if (rc != 0) return nccl_fail(n, rc, "ncclGroupEnd");
+  return AE_OK;
+}
+
 ae_status ae_count_bit_errors(ae_bits* a, ae_bits* b, ae_stats* d) {
   if (!a || !b || !d) return fail(AE_EARG, "null");
   if (a->len != b->len) return fail(AE_ELEN, "Vectors must have same length");
@@ -1279,7 +1473,7 @@ static ae_status vecstats_impl(Ctx* c, const void* p, size_t n, bool cplx, ae_ve
     const char* res = (const char*)scratch + bytes - sizeof(ae_vecstats);
     if (cudaMemcpyAsync(host_out, res, sizeof(ae_vecstats), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
       st = fail(AE_ECUDA, "VecStats read-back failed");
-    else st = ae_sync();
+    else st = sync_ctx(c);
   }
   dev_free(c, scratch);
   return st;
@@ -1691,7 +1885,7 @@ ae_status ae_f32_download(ae_f32* v, float* host, size_t n) {
   if (n != v->len) return fail(AE_ELEN, "Vectors must have same length");
   cudaSetDevice(v->c->dev);
   if (n) CK(cudaMemcpyAsync(host, v->p, n * sizeof(float), cudaMemcpyDeviceToHost, v->c->stream));
-  return ae_sync();
+  return sync_ctx(v->c);
 }
 
 ae_status ae_f32_stats(ae_f32* v, ae_vecstats* host_out) {

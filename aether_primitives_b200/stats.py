@@ -28,11 +28,71 @@ class DeviceStats:
     def evm_accumulate(self, actual: DeviceVec, reference: DeviceVec) -> None:
         call("ae_evm_accumulate", actual._h, reference._h, self._h)
 
+    def allreduce(self, comm: "Comm") -> None:
+        """In place on the device: this <- sum over the communicator's ranks (ncclAllReduce through the C ABI,
+        asynchronous on the context stream; `read()` synchronises)."""
+        call("ae_stats_allreduce", self._h, comm._h)
+
     def __del__(self):
         try:
             if self._h:
                 lib().ae_stats_free(self._h)
                 self._h = None
+        except Exception:
+            pass
+
+
+class Comm:
+    """NCCL communicator owned by the C-ABI library (`ae_comm_*`): the one collective of the path is the sum of
+    `ae_stats` over the GPUs.  One process per GPU: rank 0 creates the 128-byte id, every rank joins."""
+
+    ID_BYTES = 128
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * Comm.ID_BYTES)()
+        call("ae_comm_unique_id", buf)
+        return bytes(buf)
+
+    @classmethod
+    def init_rank(cls, uid: bytes, nranks: int, rank: int) -> "Comm":
+        assert len(uid) == cls.ID_BYTES
+        buf = (C.c_uint8 * cls.ID_BYTES).from_buffer_copy(uid)
+        h = C.c_void_p()
+        call("ae_comm_init_rank", buf, nranks, rank, C.byref(h))
+        return cls(h)
+
+    @classmethod
+    def from_torch_distributed(cls, group=None) -> "Comm":
+        """Join the ranks of an initialised torch.distributed group: torch only carries the 128-byte id from rank 0
+        to the others (the out-of-band channel); the communicator and the reduction are the library's."""
+        import torch
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.zeros(cls.ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t = torch.tensor(list(cls.unique_id()), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls.init_rank(bytes(t.cpu().tolist()), world, rank)
+
+    def info(self) -> dict:
+        n, r, d = C.c_int(), C.c_int(), C.c_int()
+        call("ae_comm_info", self._h, C.byref(n), C.byref(r), C.byref(d))
+        return {"nranks": n.value, "rank": r.value, "device": d.value}
+
+    def close(self) -> None:
+        if self._h:
+            call("ae_comm_destroy", self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 
@@ -45,8 +105,9 @@ def evm_db(err_pow: float, ref_pow: float) -> float:
 
 
 def allreduce(values: dict, group=None) -> dict:
-    """Sum {bit_errors, n_bits, err_pow, ref_pow} over ranks with torch.distributed (NCCL on GPUs,
-    gloo in the CPU tests).  <= 32 bytes per rank: the only collective of the whole path."""
+    """Host-side sum of {bit_errors, n_bits, err_pow, ref_pow} over the ranks of a torch.distributed group.  The
+    product path on GPUs is `DeviceStats.allreduce(Comm)` (NCCL through the C ABI, the counters never leave the
+    device); this helper reduces already-read values and is what the CPU tests run over gloo."""
     import torch
     import torch.distributed as dist
 

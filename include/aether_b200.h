@@ -196,6 +196,27 @@ ae_status ae_stats_read(const ae_stats* device_stats, ae_stats* host);  /* synch
 ae_status ae_count_bit_errors(ae_bits* a, ae_bits* b, ae_stats* device_stats);
 ae_status ae_evm_accumulate(ae_vec* actual, ae_vec* reference, ae_stats* device_stats);
 
+/* ---- the one collective of the path: sum of ae_stats over the GPUs, NCCL over NVLink.
+ * The reference is single-process and has no counterpart; EVM in dB follows src/lib.rs:21 from the
+ * reduced sums.  libnccl.so.2 is opened at the first call (the library itself loads without it);
+ * every failure returns AE_ENCCL with ncclGetErrorString in ae_last_error_string().
+ *   one process per GPU : rank 0 calls ae_comm_unique_id and hands the 128 bytes to every rank out of
+ *                         band (MPI, a file, torch.distributed ...); each rank then calls ae_comm_init_rank
+ *                         on its own device and ae_stats_allreduce on the context stream.
+ *   one process, n GPUs : ae_comm_init_all (ncclCommInitAll on devices 0..n-1) + ae_stats_allreduce_all,
+ *                         which issues every device's all-reduce inside one NCCL group. */
+#define AE_COMM_ID_BYTES 128
+typedef struct ae_comm ae_comm;
+ae_status ae_comm_unique_id(uint8_t id_out[AE_COMM_ID_BYTES]);
+ae_status ae_comm_init_rank(const uint8_t id[AE_COMM_ID_BYTES], int nranks, int rank, ae_comm** out);
+ae_status ae_comm_init_all(int ndev, ae_comm** comms_out /* ndev handles */);
+ae_status ae_comm_destroy(ae_comm* comm);
+ae_status ae_comm_info(const ae_comm* comm, int* nranks, int* rank, int* device);
+/* in place: device_stats <- sum over ranks; asynchronous on the device context's stream
+ * (ae_stats_read synchronises).  u64 counters are summed exactly; the two f64 sums in NCCL's order. */
+ae_status ae_stats_allreduce(ae_stats* device_stats, ae_comm* comm);
+ae_status ae_stats_allreduce_all(ae_stats** device_stats, ae_comm** comms, int ndev);
+
 /* VecStats, the README TODO "Add VecStats (f32,cf32): Min(index), Max(index), Mean(index), Power"
  * (README.md:90-92; no definition exists in the reference, so this IS the definition):
  * cf32 elements are ranked by norm_sqr = re*re + im*im (f32, unfused), f32 elements by value; ties keep
