@@ -12,12 +12,14 @@
 
 namespace ae {
 
+// WARPS >= 14 builds are LEAN (first-stage twiddles from shared memory, twiddle products recomputed): they have to fit
+// 65536 / (32 WARPS) registers
 template <int N, bool INV, bool STAGED, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 chain_x2_kernel(const __grid_constant__ ChainX2Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const X2Launch L{(int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x, (int)blockDim.x};
-  chain_x2_body<N, INV, STAGED>(p, L, smem_raw);
+  chain_x2_body<N, INV, STAGED, (WARPS >= 14)>(p, L, smem_raw);
 }
 
 bool chain_x2_supported(size_t nfft, size_t ntaps) { return nfft == 1024 && ntaps >= 1 && ntaps <= (size_t)X2Cfg<1024>::MAX_TAPS; }
@@ -53,15 +55,18 @@ static void launch_x2_dir(const ChainX2Params& p, cudaStream_t st) {
   static const char* no_tma = getenv("AE_CHAIN_NO_TMA");
   static const char* warps_env = getenv("AE_CHAIN_WARPS");
   const bool staged = ((uintptr_t)p.x % 16) == 0 && !no_tma;
-  const int warps = warps_env ? atoi(warps_env) : (staged ? 11 : 16);
+  // 8 warps (2 per sub-partition) measured best: the kernel is bound by instruction dispatch, not by latency
+  const int warps = warps_env ? atoi(warps_env) : (staged ? 8 : 12);
   if (staged) {
-    if (warps <= 8) launch_x2<INV, true, 8>(p, st);
-    else if (warps <= 10) launch_x2<INV, true, 10>(p, st);
-    else launch_x2<INV, true, 11>(p, st);
+    if (warps <= 4) launch_x2<INV, true, 4>(p, st);
+    else if (warps <= 8) launch_x2<INV, true, 8>(p, st);
+    else launch_x2<INV, true, 10>(p, st);
   } else {
     if (warps <= 8) launch_x2<INV, false, 8>(p, st);
     else if (warps <= 12) launch_x2<INV, false, 12>(p, st);
-    else launch_x2<INV, false, 16>(p, st);
+    else if (warps <= 14) launch_x2<INV, false, 14>(p, st);
+    else if (warps <= 16) launch_x2<INV, false, 16>(p, st);
+    else launch_x2<INV, false, 20>(p, st);
   }
 }
 
@@ -71,6 +76,10 @@ void launch_chain_x2(const float2* x, uint8_t* bits, size_t frames, const float2
   ChainX2Params p;
   p.x = x; p.bits = bits; p.frames = frames; p.window = window; p.tw = tw; p.taps_hi = taps_hi; p.taps_lo = taps_lo;
   p.ntaps = (int)ntaps; p.scale = scale; p.compat = compat;
+  static const char* dbg = getenv("AE_CHAIN_DEBUG");
+  p.debug = dbg ? atoi(dbg) : 0;
+  static const char* stg = getenv("AE_CHAIN_STAGGER");
+  p.stagger = stg ? atoi(stg) : 2400;
   if (inverse) launch_x2_dir<true>(p, st);
   else launch_x2_dir<false>(p, st);
 }

@@ -12,16 +12,22 @@
 //     as the two halves of f32x2 registers: every butterfly instruction does two transforms' work, the
 //     twiddle is a broadcast scalar operand.  The scalar first stage writes straight into the register
 //     halves, so no instruction is spent on packing.
-//   * N/2 = 512 = 16 * 16 * 2 points on 32 threads: a frame belongs to one warp, the two exchanges
-//     are __syncwarp()-only, warps never wait for each other and drift out of phase.
+//   * 1024 = 32 * 32 with ONE exchange.  Thread t first transforms its 32 samples x[t + 32 j] over j (the
+//     scalar radix-2 split above followed by a packed radix-16: register k0 then holds Y[2 k0] and
+//     Y[2 k0 + 1] in its two halves), multiplies by W^(t kappa) and writes them to shared memory; thread
+//     kappa reads the 32 values Z_t[kappa] back as 16 pairs (t even, t odd), runs a packed radix-16 over
+//     the pairs and combines the two halves with a scalar radix-2 (compile-time twiddles W32^c):
+//     X[kappa + 32 c].  The first build (512 = 16*16*2 per half, two exchanges) was bound by shared-memory
+//     wavefronts (ncu: l1tex data pipe 77 %, 791 wavefronts per frame); this layout needs 144 fewer.
+//     A frame belongs to one warp: the exchange is __syncwarp()-only, warps drift out of phase.
 //   * every twiddle a thread needs is fixed (it depends on the lane only): loaded once into registers.
 //   * the wrap-around correction (T(T-1)/2 complex MACs per frame, 20 % of K14's FMA-pipe time) runs on
 //     the tensor cores: with n = 8a + b it is the GEMM
 //         fix[b][a] = sum_{i'} H[b][i'] R[i'][a],   H[b][i'] = h[b+1+i'],   R[i'][a] = rt[i' - 8a],
 //     M = 16 (b, real and imaginary tap parts), N = 8 (a), K = 64, as mma.sync m16n8k8 TF32 with the
 //     3xTF32 split (hi*hi + hi*lo + lo*hi: relative error ~2^-21, FP32 class).  48 MMAs per frame.
-//   * the sub-transform leaves thread t with bins (2s, 2s+1), s = t + 32 m, in the two register halves:
-//     the four decision bytes of a register are one 32-bit store, coalesced over the warp.
+//   * thread kappa ends with bins kappa + 32 c: the two decision bytes of a bin are one 16-bit store,
+//     a warp writes 64 contiguous bytes per instruction.
 //
 // The file is also compiled for the HOST by tests/cpp/chain_x2_emu.cpp (one std::thread per CUDA
 // thread, barriers for __syncwarp/__syncthreads, an m16n8k8 emulation) so that index maps, twiddle
@@ -188,21 +194,31 @@ AE_X2_DEV void c2dft16(cx2 (&v)[16]) {
 // ---- geometry ---------------------------------------------------------------------------------------
 template <int N>
 struct X2Cfg {
-  static constexpr int N2 = N / 2;               // packed sub-transform length
-  using C = FftCfg<N2>;
-  static constexpr int T = C::T;                 // threads per frame
-  static_assert(N == 1024 && T == 32 && C::NP == 3 && C::radix(2) == 2, "K14b is laid out for N = 1024: one warp per frame, 512 = 16*16*2");
-  static constexpr int MAX_TAPS = N / 16;        // wrap-around correction needs the last N/16 bins only
-  // per-thread twiddle rows (row-major [row][t]): 16 first-stage, 6 for the second radix-16 pass, 8 for the radix-2 pass
-  static constexpr int ROW_S1 = 0, ROW_P1 = 16, ROW_P2 = 22, ROWS = 30;
+  static constexpr int T = 32;                   // threads per frame: one warp
+  static_assert(N == 1024, "K14b is laid out for N = 1024 = 32 * 32: one warp per frame");
+  static constexpr int MAX_TAPS = 64;            // wrap-around correction needs the last 64 bins only (c = 30, 31)
+  // per-thread twiddle rows (row-major [row][t]): 16 first-stage rows W_N^(t + 32 m), 6 rows W_512^(e t), e = 1,2,3,4,8,12
+  static constexpr int ROW_S1 = 0, ROW_P1 = 16, ROWS = 22;
   static constexpr int HPAD = MAX_TAPS + 8;      // zero padded tap arrays (hi / lo parts)
-  // shared memory (bytes): [taps hi: HPAD cf32][taps lo: HPAD cf32][window: N cf32][per warp: ex | rtz | fix | xin | mbar]
-  static constexpr int EX_ELEMS = C::SMEM_ELEMS;             // padded sub-positions; two float2 planes (re pairs, im pairs)
-  static constexpr int RTZ_ELEMS = 128 + 64;                 // logical index u in [0,128): u + 4 (u >> 3)
+  // shared memory (bytes): [taps hi: HPAD cf32][taps lo: HPAD cf32][window: N cf32][first-stage twiddles: 16 T cf32]
+  //                        [per warp: ex | rtz | fix | xin | mbar]
+  // exchange buffer: two float planes (re, im); Z_t[kappa] at float kappa*36 + t.  Writers (lanes = t) store 4-byte
+  // words to consecutive addresses; reader kappa fetches its row with eight 16-byte loads per plane (row stride 36
+  // floats = 9 x 16 B: the 8 lanes of a quarter-warp hit 8 different bank groups), and every 16-byte load is two
+  // ready-made (t even, t odd) register pairs.  (Dispatch cost per frame, from the SASS stall fields: 64 LDS.32 + 29
+  // MOVs = 450 cycles in the first one-exchange build, 32 LDS.128 now.)
+  static constexpr int EX_ROW = 36;                          // floats per kappa row
+  static constexpr int EX_ELEMS = 16 * EX_ROW;               // float2 per plane (= 32 rows of EX_ROW floats)
+  // rt, pre-split for 3xTF32 and laid out as mma B fragments: block j = u >> 3 (u = 64 + i, i the rt index; blocks 0..7
+  // stay zero) holds, for tig = (u & 3), the 8 floats {hi.re, lo.re, hi.im, lo.im} x {u & 4 ? 1 : 0} interleaved as
+  // (hi.re[u], hi.re[u+4], lo.re[u], lo.re[u+4], hi.im[u], hi.im[u+4], lo.im[u], lo.im[u+4]): two 16-byte loads are the
+  // four fragment register pairs of one k-step.  Block stride 36 floats: lanes g, g+1 fall into different bank groups.
+  static constexpr int RTZ_BLOCK = 36;                       // floats per block of 8 rt entries (32 + 4 of skew)
+  static constexpr int RTZ_ELEMS = 16 * RTZ_BLOCK / 2;       // float2
   static constexpr int FIX_ELEMS = 80;                       // n in [0,64): n + 4 (n >> 4)
-  static constexpr size_t HEAD_BYTES = (size_t)(2 * HPAD + N) * sizeof(float2);
+  static constexpr size_t HEAD_BYTES = (size_t)(2 * HPAD + N + 16 * T) * sizeof(float2);   // + first-stage twiddle rows (LEAN)
   static constexpr size_t warp_bytes(bool staged) {
-    return (size_t)EX_ELEMS * 16 + (size_t)(RTZ_ELEMS + FIX_ELEMS) * sizeof(float2) + (staged ? (size_t)N * sizeof(float2) : 0) + 16;
+    return (size_t)2 * EX_ELEMS * sizeof(float2) + (size_t)(RTZ_ELEMS + FIX_ELEMS) * sizeof(float2) + (staged ? (size_t)N * sizeof(float2) : 0) + 16;
   }
   static constexpr size_t smem_bytes(int warps, bool staged) { return HEAD_BYTES + (size_t)warps * warp_bytes(staged); }
 };
@@ -220,95 +236,100 @@ struct ChainX2Params {
   int ntaps;
   float scale;
   int compat;
+  int debug;              // developer switch for timing experiments (AE_CHAIN_DEBUG): 1 = skip transform A and the fix-up, 2 = skip B
+  int stagger;            // cycles between the starts of the warps that share an SM sub-partition (see chain_x2_body)
 };
 
 // the lane's twiddles, loaded once
 struct X2Tw {
-  float2 s1[16];   // W_N^(t + T m)              first (radix-2, scalar) stage
-  float2 wl[4];    // W_N2^(b u), b = 1..3       second radix-16 pass, u = (t mod 16) * N2/256
-  float2 wh[4];    // W_N2^(4 a u), a = 1..3
-  float2 p2[8];    // W_N2^(t + T q)             last (radix-2) pass
+  float2 s1[16];   // W_N^(t + 32 m)             first (radix-2, scalar) stage, odd half
+  float2 wl[4];    // W_512^(b t), b = 1..3      between the stages: Z[2 k0 + b'] = W_512^(k0 t) Y[2 k0 + b'],
+  float2 wh[4];    // W_512^(4 a t), a = 1..3    W^(4a+b) = W^(4a) W^b
 };
 
-// The exchange buffer is PLANAR: the (x, y) pair of real parts of sub-position i at ex[i], the pair of
-// imaginary parts at ex[EX_ELEMS + i].  A 16-byte interleaved layout needs the two register pairs of a
-// value in one aligned register quad, which costs four MOVs per store (measured in the first build's SASS).
-template <int EX>
-AE_X2_DEV void c2store(float2* ex, int i, cx2 v) { ex[i] = v.re; ex[EX + i] = v.im; }
-template <int EX>
-AE_X2_DEV cx2 c2load(const float2* ex, int i) { return cx2{ex[i], ex[EX + i]}; }
+// cos / sin of 2 pi c / 32, c = 0..15 (twiddles of the final radix-2 combine)
+__host__ __device__ constexpr float x2_c32(int c) {
+  constexpr float v[16] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f, 0.70710678118654752440f,
+                           0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f, 0.0f, -0.19509032201612826785f,
+                           -0.38268343236508977173f, -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                           -0.92387953251128675613f, -0.98078528040323044913f};
+  return v[c];
+}
+__host__ __device__ constexpr float x2_s32(int c) { return c <= 8 ? x2_c32(8 - c) : x2_c32(c - 8); }   // sin t = cos(t - pi/2)
 
-// Packed N/2-point transform of v (register m <-> sub-position t + m T, in and out) through the warp's
-// exchange buffer.  TAIL: only register 15 (the last T sub-bins of both halves) is needed afterwards;
-// everything is unrolled register code, so the compiler drops what does not feed v[15], and the
-// stores/loads of the second exchange that are never consumed are skipped by hand.
-template <int N, bool INV, bool TAIL>
-AE_X2_DEV void x2_fft(cx2 (&v)[16], float2* ex, const X2Tw& tw, int t) {
+// Second half of the frame transform.  In: v[k0] = (Y[2 k0], Y[2 k0 + 1]) of thread t, Y = DFT_32 over j of x[t + 32 j]
+// (the odd half already carries W_N^t).  Out: y[c] = X[kappa + 32 c] for thread kappa = t.
+// TAIL: only y[30], y[31] are produced (the last 64 bins of the frame, all the wrap-around correction needs).
+// LEAN: the nine twiddle products are recomputed per transform (an opaque move keeps the compiler from hoisting them
+// out of the frame loop into 18 more registers).
+AE_X2_DEV float2 x2_opaque(float2 w) {
+#ifndef AE_HOST_EMU
+  asm volatile("" : "+f"(w.x), "+f"(w.y));
+#endif
+  return w;
+}
+template <int N, bool INV, bool TAIL, bool LEAN>
+AE_X2_DEV void x2_second_stage(cx2 (&v)[16], float2 (&y)[32], float2* ex, const X2Tw& tw, int t) {
   using XC = X2Cfg<N>;
-  constexpr int T = XC::T;
   constexpr int EX = XC::EX_ELEMS;
-  // pass 0: radix 16 over sub-positions t + m T, no twiddles; output r -> position 16 t + r
-  c2dft16<INV>(v);
+  // Z_t[2 k0 + b] = W_512^(k0 t) v[k0].b, stored at float (k0*33 + t)*2 + b of each plane
   {
-    const int a0 = 17 * t;
+    // twiddle and store element by element: the 4-byte stores are spaced by the multiplies instead of queueing up
+    float* wr = reinterpret_cast<float*>(ex) + t;
+    float* wi = wr + 2 * EX;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) c2store<EX>(ex, a0 + r, v[r]);
-  }
-  x2_syncwarp();
-  {
-    const int a0 = fft_pad(t);
-    constexpr int STEP = T + T / 16;
-#pragma unroll
-    for (int m = 0; m < 16; ++m) v[m] = c2load<EX>(ex, a0 + m * STEP);
-  }
-  x2_syncwarp();
-  // pass 1: radix 16, NS = 16, k = t mod 16: v[r] *= W^(r u); W^(4a+b) = W^(4a) W^b
-  {
-    const int k = t & 15;
-#pragma unroll
-    for (int r = 1; r < 16; ++r) {
-      const int a = r >> 2, bb = r & 3;
-      float2 w;
-      if (a == 0) w = tw.wl[bb];
-      else if (bb == 0) w = tw.wh[a];
-      else w = cx_mul(tw.wh[a], tw.wl[bb]);
-      v[r] = c2mul_tw<INV>(v[r], w);
-    }
-    c2dft16<INV>(v);
-    const int a0 = fft_pad((t - k) * 16 + k);
-#pragma unroll
-    for (int r = TAIL ? 14 : 0; r < 16; ++r) c2store<EX>(ex, a0 + r * 17, v[r]);  // TAIL: the last pass reads registers 7 and 15 only
-  }
-  x2_syncwarp();
-  {
-    const int a0 = fft_pad(t);
-    constexpr int STEP = T + T / 16;
-    if (TAIL) {
-      v[7] = c2load<EX>(ex, a0 + 7 * STEP);
-      v[15] = c2load<EX>(ex, a0 + 15 * STEP);
-    } else {
-#pragma unroll
-      for (int m = 0; m < 16; ++m) v[m] = c2load<EX>(ex, a0 + m * STEP);
+    for (int r = 0; r < 16; ++r) {
+      if (r > 0) {
+        const int a = r >> 2, bb = r & 3;
+        float2 w;
+        if (a == 0) w = tw.wl[bb];
+        else if (bb == 0) w = tw.wh[a];
+        else w = cx_mul(LEAN ? x2_opaque(tw.wh[a]) : tw.wh[a], tw.wl[bb]);
+        v[r] = c2mul_tw<INV>(v[r], w);
+      }
+      wr[(2 * r) * XC::EX_ROW] = v[r].re.x; wr[(2 * r + 1) * XC::EX_ROW] = v[r].re.y;
+      wi[(2 * r) * XC::EX_ROW] = v[r].im.x; wi[(2 * r + 1) * XC::EX_ROW] = v[r].im.y;
     }
   }
-  // pass 2: radix 2 on (q, q + 8): v[q+8] *= W_N2^(t + T q)
-  if (TAIL) {
-    v[15] = c2sub(v[7], c2mul_tw<INV>(v[15], tw.p2[7]));
-  } else {
+  x2_syncwarp();
+  // thread kappa gathers its row Z_t[kappa], t = 0..31: pairs (t = 2u, 2u + 1) = halves of the packed registers
+  {
+    const float4* pr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ex) + t * XC::EX_ROW);
+    const float4* pi = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ex) + 2 * EX + t * XC::EX_ROW);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const cx2 b = c2mul_tw<INV>(v[q + 8], tw.p2[q]);
-      const cx2 a = v[q];
-      v[q] = c2add(a, b);
-      v[q + 8] = c2sub(a, b);
+      const float4 a = pr[q], b = pi[q];
+      v[2 * q] = cx2{make_float2(a.x, a.y), make_float2(b.x, b.y)};
+      v[2 * q + 1] = cx2{make_float2(a.z, a.w), make_float2(b.z, b.w)};
     }
+  }
+  // X[kappa + 32 c] = sum_t Z_t W_32^(t c) = E[c mod 16] + W_32^c O[c mod 16], E / O = DFT_16 over the even / odd t
+  c2dft16<INV>(v);
+  if (TAIL) {
+    // c = 30, 31: E[c0] - W_32^c0 O[c0], c0 = 14, 15
+    static_for<14, 16>([&](auto cc) {
+      constexpr int c0 = decltype(cc)::value;
+      const float2 o = mul_w<INV>(make_float2(v[c0].re.y, v[c0].im.y), x2_c32(c0), x2_s32(c0));
+      y[c0 + 16] = make_float2(v[c0].re.x - o.x, v[c0].im.x - o.y);
+    });
+  } else {
+    static_for<0, 16>([&](auto cc) {
+      constexpr int c0 = decltype(cc)::value;
+      float2 o = make_float2(v[c0].re.y, v[c0].im.y);
+      if constexpr (c0 == 8) o = mul_mi<INV>(o);
+      else if constexpr (c0 != 0) o = mul_w<INV>(o, x2_c32(c0), x2_s32(c0));
+      y[c0] = make_float2(v[c0].re.x + o.x, v[c0].im.x + o.y);
+      y[c0 + 16] = make_float2(v[c0].re.x - o.x, v[c0].im.x - o.y);
+    });
   }
 }
 
 // first stage: radix-2 DIF split of the frame into the even-bin (x half) and odd-bin (y half) inputs;
 // WIN multiplies by the FIR window first
-template <int N, bool INV, bool WIN>
-AE_X2_DEV void x2_stage1(cx2 (&v)[16], const float2* __restrict__ src, const float2* __restrict__ win, const X2Tw& tw, int t) {
+// LEAN reads the odd half's twiddles from the shared table s1tab[m][t] instead of 32 registers
+template <int N, bool INV, bool WIN, bool LEAN>
+AE_X2_DEV void x2_stage1(cx2 (&v)[16], const float2* __restrict__ src, const float2* __restrict__ win, const X2Tw& tw,
+                         const float2* __restrict__ s1tab, int t) {
   constexpr int T = X2Cfg<N>::T;
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
@@ -319,26 +340,29 @@ AE_X2_DEV void x2_stage1(cx2 (&v)[16], const float2* __restrict__ src, const flo
       b = cx_mul(b, win[s + N / 2]);
     }
     const float2 e = make_float2(a.x + b.x, a.y + b.y), d = make_float2(a.x - b.x, a.y - b.y);
-    const float2 o = mul_tw<INV>(d, tw.s1[m]);
+    const float2 o = mul_tw<INV>(d, LEAN ? s1tab[s] : tw.s1[m]);
     v[m] = cx2{make_float2(e.x, o.x), make_float2(e.y, o.y)};
   }
 }
 
-// The four decision bytes of one packed register (bins 2s and 2s+1): byte = sign of re / im, the im
-// byte is 2 (compat=reference, idx & 2) or 1 (corrected); `mask` = 0x02010201 / 0x01010101
-AE_X2_DEV uint32_t x2_sign_word(cx2 v, uint32_t mask) {
-  const uint32_t p1 = x2_prmt(__float_as_uint(v.re.x), __float_as_uint(v.im.x), 0x00FBu);  // bytes 0,1 <- sign(re.x), sign(im.x)
-  const uint32_t p2 = x2_prmt(__float_as_uint(v.re.y), __float_as_uint(v.im.y), 0xFB00u);  // bytes 2,3 <- sign(re.y), sign(im.y)
-  return (p1 & (mask & 0xffffu)) | (p2 & (mask & 0xffff0000u));
+// The two decision bytes of one bin as a little-endian u16: byte = sign of re / im, the im byte is 2
+// (compat=reference, idx & 2) or 1 (corrected); `mask` = 0x0201 / 0x0101
+AE_X2_DEV uint32_t x2_sign_pair(float2 v, uint32_t mask) {
+  return x2_prmt(__float_as_uint(v.x), __float_as_uint(v.y), 0x00FBu) & mask;   // bytes 0,1 <- sign(re), sign(im) replicated
 }
-AE_X2_DEV uint32_t x2_exact_word(cx2 v, unsigned hi_shift) {
-  const unsigned e = demod_qpsk_exact_slow(make_float2(v.re.x, v.im.x)), o = demod_qpsk_exact_slow(make_float2(v.re.y, v.im.y));
-  return qpsk_pair_from_index(e, hi_shift) | (qpsk_pair_from_index(o, hi_shift) << 16);
+
+// rt entry u, split for the 3xTF32 products (hi = the value truncated to TF32's 10 mantissa bits, lo = value - hi) and
+// written into the fragment-ready layout described at X2Cfg::RTZ_BLOCK
+template <int BLOCK>
+AE_X2_DEV void x2_store_rt(float* rtz, int u, float2 a) {
+  const float hx = __uint_as_float(__float_as_uint(a.x) & 0xffffe000u), hy = __uint_as_float(__float_as_uint(a.y) & 0xffffe000u);
+  float* q = rtz + (u >> 3) * BLOCK + 8 * (u & 3) + ((u >> 2) & 1);
+  q[0] = hx; q[2] = a.x - hx; q[4] = hy; q[6] = a.y - hy;
 }
 
 struct X2Launch { int tid, bid, nblocks, nthreads; };
 
-template <int N, bool INV, bool STAGED>
+template <int N, bool INV, bool STAGED, bool LEAN = false>
 AE_X2_DEV void chain_x2_body(const ChainX2Params& p, const X2Launch& L, unsigned char* smem_raw) {
   using XC = X2Cfg<N>;
   constexpr int T = XC::T;
@@ -346,8 +370,9 @@ AE_X2_DEV void chain_x2_body(const ChainX2Params& p, const X2Launch& L, unsigned
   float2* hhi = reinterpret_cast<float2*>(smem_raw);
   float2* hlo = hhi + XC::HPAD;
   float2* win = hlo + XC::HPAD;
+  float2* s1tab = win + N;                                                        // [m][t] = W_N^(t + 32 m) = W_N^s
   unsigned char* mine = smem_raw + XC::HEAD_BYTES + (size_t)warp * XC::warp_bytes(STAGED);
-  float2* ex = reinterpret_cast<float2*>(mine);
+  float2* ex = reinterpret_cast<float2*>(mine);                                  // two planes of EX_ELEMS float2
   float2* rtz = ex + 2 * XC::EX_ELEMS;
   float2* fixb = rtz + XC::RTZ_ELEMS;
   float2* xin = fixb + XC::FIX_ELEMS;                                           // STAGED only
@@ -355,15 +380,14 @@ AE_X2_DEV void chain_x2_body(const ChainX2Params& p, const X2Launch& L, unsigned
 
   for (int i = L.tid; i < XC::HPAD; i += L.nthreads) { hhi[i] = p.taps_hi[i]; hlo[i] = p.taps_lo[i]; }
   for (int i = L.tid; i < N; i += L.nthreads) win[i] = p.window[i];
+  for (int i = L.tid; i < 16 * T; i += L.nthreads) s1tab[i] = p.tw[XC::ROW_S1 * T + i];
   for (int i = t; i < XC::RTZ_ELEMS; i += 32) rtz[i] = make_float2(0.0f, 0.0f);   // logical [0,64) stays zero for ever
   X2Tw tw;
 #pragma unroll
-  for (int m = 0; m < 16; ++m) tw.s1[m] = p.tw[(XC::ROW_S1 + m) * T + t];
+  for (int m = 0; m < 16; ++m) tw.s1[m] = LEAN ? make_float2(0.0f, 0.0f) : p.tw[(XC::ROW_S1 + m) * T + t];
 #pragma unroll
   for (int i = 1; i < 4; ++i) { tw.wl[i] = p.tw[(XC::ROW_P1 + i - 1) * T + t]; tw.wh[i] = p.tw[(XC::ROW_P1 + i + 2) * T + t]; }
   tw.wl[0] = tw.wh[0] = make_float2(1.0f, 0.0f);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) tw.p2[q] = p.tw[(XC::ROW_P2 + q) * T + t];
 
   const size_t stride = (size_t)L.nblocks * nwarps;
   size_t frame = (size_t)L.bid * nwarps + warp;
@@ -382,10 +406,23 @@ AE_X2_DEV void chain_x2_body(const ChainX2Params& p, const X2Launch& L, unsigned
 #endif
   }
   x2_syncthreads();
+#ifndef AE_HOST_EMU
+  // Stagger.  Every warp runs the same periodic mix of an FMA-pipe phase (butterflies) and a phase that
+  // does not need that pipe (shared-memory exchange, decisions, MMA).  Warps that start together stay
+  // together: the pipe is shared fairly while both want it, so their distance never changes, and the pipe
+  // idles whenever they are all in the other phase (measured: throughput independent of the warp count,
+  // FMA pipe 47 % busy).  Starting the warps of one sub-partition (warp id mod 4) a fraction of a frame
+  // apart makes the phases of one warp fall into the gaps of the others.
+  if (p.stagger > 0) {
+    const long long wait = (long long)(warp >> 2) * p.stagger;
+    const long long t0 = clock64();
+    while (clock64() - t0 < wait) {}
+  }
+#endif
 
   const int g = t >> 2, tig = t & 3;                       // mma.sync fragment coordinates
   const int ksteps = (p.ntaps - 1 + 7) >> 3;               // k-steps of 8 that hold non-zero taps (<= 8)
-  const uint32_t mask = p.compat == AE_COMPAT_REFERENCE ? 0x02010201u : 0x01010101u;
+  const uint32_t mask = p.compat == AE_COMPAT_REFERENCE ? 0x0201u : 0x0101u;
   const unsigned hi_shift = p.compat == AE_COMPAT_REFERENCE ? 9u : 8u;
   uint32_t phase = 0;
   for (; frame < p.frames; frame += stride) {
@@ -402,46 +439,65 @@ AE_X2_DEV void chain_x2_body(const ChainX2Params& p, const X2Launch& L, unsigned
       src = p.x + frame * N;
     }
     cx2 v[16];
-    // ---- A = DFT(x), last T sub-bins of both halves: bins N - 2T .. N-1 ----
-    x2_stage1<N, INV, false>(v, src, nullptr, tw, t);
-    x2_fft<N, INV, true>(v, ex, tw, t);
+    float2 y[32];
+    float2 fx0 = make_float2(0.0f, 0.0f), fx1 = fx0;
+#ifdef AE_CHAIN_DEBUG_BUILD
+    if (!(p.debug & 1))
+#endif
     {
-      // v[15]: x half = A[N - 2T + 2t] -> rt index i = 2T - 1 - 2t, y half = A[N - 2T + 2t + 1] -> i = 2T - 2 - 2t.
-      // rt[i] = scale * A[N-1-i] lives at logical index u = 64 + i; (u_y, u_x) = (even, odd) share a 16-byte slot.
-      float2 ax = cx_scale_exact(make_float2(v[15].re.x, v[15].im.x), p.scale);
-      const float2 ay = cx_scale_exact(make_float2(v[15].re.y, v[15].im.y), p.scale);
-      if (t == 0) ax = make_float2(0.0f, 0.0f);            // i = 2T-1 = 63 is never used (taps beyond it are zero): keep 0 * inf out
-      const int u = 64 + 2 * T - 2 - 2 * t;
-      *reinterpret_cast<float4*>(rtz + x2_rtz_phys(u)) = make_float4(ay.x, ay.y, ax.x, ax.y);
+    // ---- A = DFT(x), bins kappa + 32 c for c = 30, 31: the last 64 bins ----
+    x2_stage1<N, INV, false, LEAN>(v, src, nullptr, tw, s1tab, t);
+    c2dft16<INV>(v);
+    x2_second_stage<N, INV, true, LEAN>(v, y, ex, tw, t);
+    {
+      // rt[i] = scale * A[N-1-i] at logical index u = 64 + i: y[31] = A[992 + t] -> i = 31 - t, y[30] = A[960 + t] -> i = 63 - t
+      float2 a30 = cx_scale_exact(y[30], p.scale);
+      const float2 a31 = cx_scale_exact(y[31], p.scale);
+      if (t == 0) a30 = make_float2(0.0f, 0.0f);           // i = 63 is never used (taps beyond it are zero): keep 0 * inf out
+      x2_store_rt<XC::RTZ_BLOCK>(reinterpret_cast<float*>(rtz), 64 + 31 - t, a31);
+      x2_store_rt<XC::RTZ_BLOCK>(reinterpret_cast<float*>(rtz), 64 + 63 - t, a30);
     }
     x2_syncwarp();
-    // ---- wrap-around correction on the tensor cores (3xTF32) ----
-    float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};   // H * Re(R), H * Im(R); rows 0-7: Re(H), rows 8-15: Im(H)
-    for (int ks = 0; ks < ksteps; ++ks) {
+    // ---- wrap-around correction on the tensor cores (3xTF32); six independent accumulator chains ----
+    float d1[3][4], d2[3][4];   // H * Re(R), H * Im(R); rows 0-7: Re(H), rows 8-15: Im(H); [0] lo*hi, [1] hi*lo, [2] hi*hi
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d1[i][j] = d2[i][j] = 0.0f;
+    auto mma_step = [&](int ks) {
       const int hi0 = g + tig + 8 * ks + 1;                // A fragment: rows (g, g+8) = (Re h, Im h)[g + 1 + col], cols tig, tig + 4
       const float2 ah0 = hhi[hi0], ah1 = hhi[hi0 + 4], al0 = hlo[hi0], al1 = hlo[hi0 + 4];
       const uint32_t a_hi[4] = {__float_as_uint(ah0.x), __float_as_uint(ah0.y), __float_as_uint(ah1.x), __float_as_uint(ah1.y)};
       const uint32_t a_lo[4] = {__float_as_uint(al0.x), __float_as_uint(al0.y), __float_as_uint(al1.x), __float_as_uint(al1.y)};
-      const int u = 64 + 8 * (ks - g) + tig;               // B fragment: R[k][n] = rt[8 ks + k - 8 n], k = tig (+4), n = g
-      const float2 r0 = rtz[x2_rtz_phys(u)], r1 = rtz[x2_rtz_phys(u + 4)];
-      uint32_t bh[2], bl[2], ch[2], cl[2];
-      bh[0] = __float_as_uint(r0.x) & 0xffffe000u; bl[0] = __float_as_uint(r0.x - __uint_as_float(bh[0]));
-      bh[1] = __float_as_uint(r1.x) & 0xffffe000u; bl[1] = __float_as_uint(r1.x - __uint_as_float(bh[1]));
-      ch[0] = __float_as_uint(r0.y) & 0xffffe000u; cl[0] = __float_as_uint(r0.y - __uint_as_float(ch[0]));
-      ch[1] = __float_as_uint(r1.y) & 0xffffe000u; cl[1] = __float_as_uint(r1.y - __uint_as_float(ch[1]));
-      x2_mma(d1, a_lo, bh); x2_mma(d1, a_hi, bl); x2_mma(d1, a_hi, bh);
-      x2_mma(d2, a_lo, ch); x2_mma(d2, a_hi, cl); x2_mma(d2, a_hi, ch);
+      // B fragment: R[k][n] = rt[8 ks + k - 8 n], k = tig (+4), n = g  ->  block 8 + ks - g, slot tig
+      const float4* rb = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rtz) + (8 + ks - g) * XC::RTZ_BLOCK + 8 * tig);
+      const float4 r0 = rb[0], r1 = rb[1];
+      const uint32_t bh[2] = {__float_as_uint(r0.x), __float_as_uint(r0.y)}, bl[2] = {__float_as_uint(r0.z), __float_as_uint(r0.w)};
+      const uint32_t ch[2] = {__float_as_uint(r1.x), __float_as_uint(r1.y)}, cl[2] = {__float_as_uint(r1.z), __float_as_uint(r1.w)};
+      x2_mma(d1[0], a_lo, bh); x2_mma(d1[1], a_hi, bl); x2_mma(d1[2], a_hi, bh);
+      x2_mma(d2[0], a_lo, ch); x2_mma(d2[1], a_hi, cl); x2_mma(d2[2], a_hi, ch);
+    };
+    if (ksteps == 8) {                                     // 57..64 taps: straight-line code, no per-step branch
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) mma_step(ks);
+    } else {
+#pragma unroll 1
+      for (int ks = 0; ks < ksteps; ++ks) mma_step(ks);
     }
     {
       // accumulator (row g, col 2 tig + j): Re(H) part for n = 8 (2 tig + j) + g; row g + 8: Im(H) part
+      float e1[4], e2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { e1[j] = (d1[0][j] + d1[1][j]) + d1[2][j]; e2[j] = (d2[0][j] + d2[1][j]) + d2[2][j]; }
       const int n1 = 16 * tig + g;
-      fixb[x2_fix_phys(n1)] = make_float2(d1[0] - d2[2], d1[2] + d2[0]);
-      fixb[x2_fix_phys(n1 + 8)] = make_float2(d1[1] - d2[3], d1[3] + d2[1]);
+      fixb[x2_fix_phys(n1)] = make_float2(e1[0] - e2[2], e1[2] + e2[0]);
+      fixb[x2_fix_phys(n1 + 8)] = make_float2(e1[1] - e2[3], e1[3] + e2[1]);
     }
     x2_syncwarp();
-    const float4 fx = *reinterpret_cast<const float4*>(fixb + x2_fix_phys(2 * t));   // fix[2t], fix[2t+1]
+    fx0 = fixb[x2_fix_phys(t)]; fx1 = fixb[x2_fix_phys(32 + t)];   // bins t (c = 0) and 32 + t (c = 1)
+    }
     // ---- B = DFT(x .* w): circular convolution of scale * X with the taps ----
-    x2_stage1<N, INV, true>(v, src, win, tw, t);
+    x2_stage1<N, INV, true, LEAN>(v, src, win, tw, s1tab, t);
     if (STAGED) {
       x2_syncwarp();                                       // every lane has consumed the staged frame
       if (t == 0 && frame + stride < p.frames) {
@@ -453,32 +509,33 @@ AE_X2_DEV void chain_x2_body(const ChainX2Params& p, const X2Launch& L, unsigned
 #endif
       }
     }
-    x2_fft<N, INV, false>(v, ex, tw, t);
-    v[0].re.x -= fx.x; v[0].im.x -= fx.y;                  // bins 2t, 2t+1 < 2T are the only ones with wrap-around terms
-    v[0].re.y -= fx.z; v[0].im.y -= fx.w;
+    c2dft16<INV>(v);
+    x2_second_stage<N, INV, false, LEAN>(v, y, ex, tw, t);
+    y[0].x -= fx0.x; y[0].y -= fx0.y;                      // bins < 64 are the only ones with wrap-around terms
+    y[1].x -= fx1.x; y[1].y -= fx1.y;
     // ---- hard decisions (src/modulation.rs:33-56) ----
     // The sign test is the reference's answer whenever min(|re|,|im|) > 2^-21 (1 + max(|re|,|im|))^2
     // (common.cuh).  The bound is monotone in max, so one test per thread with the maximum and minimum
     // over all 64 of its components is sufficient; NaN propagates through the maximum and fails it.
     float mx = 0.0f, mn = 3.0e38f;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      mx = x2_fmax3_nan(mx, fabsf(v[m].re.x), fabsf(v[m].re.y));
-      mx = x2_fmax3_nan(mx, fabsf(v[m].im.x), fabsf(v[m].im.y));
-      mn = x2_fmin3(mn, fabsf(v[m].re.x), fabsf(v[m].re.y));
-      mn = x2_fmin3(mn, fabsf(v[m].im.x), fabsf(v[m].im.y));
+    for (int c = 0; c < 32; ++c) {
+      mx = x2_fmax3_nan(mx, fabsf(y[c].x), fabsf(y[c].y));
+      mn = x2_fmin3(mn, fabsf(y[c].x), fabsf(y[c].y));
     }
     const float uu = fmaf(mx, 6.9053396600248786e-4f, 6.9053396600248786e-4f);  // 2^-10.5 (1 + max)
-    uint32_t* out = reinterpret_cast<uint32_t*>(p.bits + 2 * frame * (size_t)N);
+    uint16_t* out = reinterpret_cast<uint16_t*>(p.bits + 2 * frame * (size_t)N);
     if (mn > uu * uu) {
 #pragma unroll
-      for (int m = 0; m < 16; ++m) out[t + m * T] = x2_sign_word(v[m], mask);
+      for (int c = 0; c < 32; ++c) out[t + 32 * c] = (uint16_t)x2_sign_pair(y[c], mask);
     } else {
       // rare: near an axis, NaN or inf somewhere in this thread's bins -> per-symbol test, exact path where it fails
+#pragma unroll 1
+      for (int c = 0; c < 32; ++c) {
+        float2 s = y[0];
 #pragma unroll
-      for (int m = 0; m < 16; ++m) {
-        const bool ok = qpsk_fast_ok(make_float2(v[m].re.x, v[m].im.x)) && qpsk_fast_ok(make_float2(v[m].re.y, v[m].im.y));
-        out[t + m * T] = ok ? x2_sign_word(v[m], mask) : x2_exact_word(v[m], hi_shift);
+        for (int k = 1; k < 32; ++k) s = (c == k) ? y[k] : s;   // select without dynamic register indexing
+        out[t + 32 * c] = (uint16_t)(qpsk_fast_ok(s) ? x2_sign_pair(s, mask) : qpsk_pair_from_index(demod_qpsk_exact_slow(s), hi_shift));
       }
     }
     x2_syncwarp();                                         // the exchange buffer is rewritten by the next frame

@@ -17,7 +17,7 @@ inline void chain_x2_twiddles(size_t nfft, std::vector<float2>& out) {
   out.clear();
   if (nfft != 1024) return;
   using XC = X2Cfg<1024>;
-  constexpr int N = 1024, N2 = XC::N2, T = XC::T;
+  constexpr int N = 1024, T = XC::T;
   out.assign((size_t)XC::ROWS * T, make_float2(1.f, 0.f));
   auto W = [](long long e, long long len) {
     const double a = -2.0 * 3.14159265358979323846 * (double)(e % len) / (double)len;
@@ -25,10 +25,8 @@ inline void chain_x2_twiddles(size_t nfft, std::vector<float2>& out) {
   };
   for (int t = 0; t < T; ++t) {
     for (int m = 0; m < 16; ++m) out[(size_t)(XC::ROW_S1 + m) * T + t] = W(t + (long long)T * m, N);
-    const long long u = (long long)(t & 15) * (N2 / 256);   // second radix-16 pass: NS = 16, TWS = N2 / (16 * 16)
-    const int mult[6] = {1, 2, 3, 4, 8, 12};
-    for (int e = 0; e < 6; ++e) out[(size_t)(XC::ROW_P1 + e) * T + t] = W(mult[e] * u, N2);
-    for (int q = 0; q < 8; ++q) out[(size_t)(XC::ROW_P2 + q) * T + t] = W(t + (long long)T * q, N2);
+    const int mult[6] = {1, 2, 3, 4, 8, 12};   // Z[2 k0 + b] = W_512^(k0 t) Y[2 k0 + b]; k0 = 4a + b' from W^(4a t) W^(b' t)
+    for (int e = 0; e < 6; ++e) out[(size_t)(XC::ROW_P1 + e) * T + t] = W((long long)mult[e] * t, N / 2);
   }
 }
 

@@ -5,7 +5,7 @@
 // the kernel's index maps, twiddle rows and fragment layouts are checked without a GPU.
 //
 // usage: chain_x2_emu <in.bin> <out.bin>
-//   in.bin : int32 header {nfft, ntaps, frames, compat, inverse, staged, warps, blocks}, float32 scale,
+//   in.bin : int32 header {nfft, ntaps, frames, compat, inverse, staged (bit 0) | lean (bit 1), warps, blocks}, float32 scale,
 //            frames*nfft cf32 samples, ntaps cf32 taps
 //   out.bin: 2*frames*nfft decision bytes
 #define AE_HOST_EMU 1
@@ -125,10 +125,10 @@ int main(int argc, char** argv) {
 
   ae::ChainX2Params p;
   p.x = x.data(); p.bits = bits.data(); p.frames = (size_t)frames; p.window = window.data(); p.tw = tw.data();
-  p.taps_hi = hi.data(); p.taps_lo = lo.data(); p.ntaps = ntaps; p.scale = scale; p.compat = compat;
+  p.taps_hi = hi.data(); p.taps_lo = lo.data(); p.ntaps = ntaps; p.scale = scale; p.compat = compat; p.debug = 0; p.stagger = 0;
 
   using XC = ae::X2Cfg<1024>;
-  const size_t smem = XC::smem_bytes(warps, staged != 0);
+  const size_t smem = XC::smem_bytes(warps, (staged & 1) != 0);
   for (int b = 0; b < blocks; ++b) {
     std::vector<unsigned char> sm(smem + 16);
     unsigned char* base = sm.data() + ((16 - ((uintptr_t)sm.data() & 15)) & 15);
@@ -141,8 +141,16 @@ int main(int argc, char** argv) {
       th.emplace_back([&, tid]() {
         tl_cta = &cta; tl_warp = &cta.warps[tid >> 5]; tl_lane = tid & 31;
         const ae::X2Launch L{tid, b, blocks, 32 * warps};
-        if (inverse) { if (staged) ae::chain_x2_body<1024, true, true>(p, L, base); else ae::chain_x2_body<1024, true, false>(p, L, base); }
-        else { if (staged) ae::chain_x2_body<1024, false, true>(p, L, base); else ae::chain_x2_body<1024, false, false>(p, L, base); }
+        const bool stg = (staged & 1) != 0, lean = (staged & 2) != 0;   // bit 1: LEAN build (twiddles from shared memory)
+        if (inverse) {
+          if (stg) ae::chain_x2_body<1024, true, true, false>(p, L, base);
+          else if (lean) ae::chain_x2_body<1024, true, false, true>(p, L, base);
+          else ae::chain_x2_body<1024, true, false, false>(p, L, base);
+        } else {
+          if (stg) ae::chain_x2_body<1024, false, true, false>(p, L, base);
+          else if (lean) ae::chain_x2_body<1024, false, false, true>(p, L, base);
+          else ae::chain_x2_body<1024, false, false, false>(p, L, base);
+        }
       });
     }
     for (auto& t : th) t.join();

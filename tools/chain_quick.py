@@ -25,14 +25,33 @@ ch = FftFirDemod(n, make_taps(ntaps), ae.Scale.SN)
 for _ in range(3):
     ch.run(d_in, d_bits)
 torch.cuda.synchronize()
+# SM clock while the kernel runs (NVML, 5 ms period)
+import threading
+clk, stop = [], threading.Event()
+def _sample():
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(0)
+        while not stop.is_set():
+            clk.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            time.sleep(0.005)
+    except Exception:
+        pass
+th = threading.Thread(target=_sample, daemon=True)
+th.start()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-K = 10
+K = int(os.environ.get("REPS", "10"))
 e0.record()
 for _ in range(K):
     ch.run(d_in, d_bits)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
+stop.set()
+th.join(timeout=1)
 print("ntaps=%d" % ntaps, end="  ")
+if clk:
+    print("sm_mhz median %d min %d" % (sorted(clk)[len(clk) // 2], min(clk)), end="  ")
 print("chain: %.3f ms  %.1f Gsamples/s  %.1f%% of 6534 GB/s" % (ms, frames * n / ms / 1e6, 10 * frames * n / ms / 1e6 / 6534.1 * 100))
 # correctness is the job of tests/ (this helper only times the kernel)
