@@ -106,6 +106,7 @@ _SIGS = {
     "ae_fir_create": (None, [_P, _SZ, _I, C.POINTER(_P)]),
     "ae_fir_destroy": (None, [_P]),
     "ae_fir_ntaps": (_SZ, [_P]),
+    "ae_fir_block_hop": (_SZ, [_P]),
     "ae_fir_reset": (None, [_P]),
     "ae_fir_exec": (None, [_P, _P, _P, _SZ]),
     "ae_interpolate": (None, [_P, _P, _SZ, _I]),

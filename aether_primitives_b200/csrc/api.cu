@@ -921,26 +921,31 @@ ae_status ae_fir_create(const ae_cf32* taps_host, size_t ntaps, int mode, ae_fir
   ae_fir* f = new ae_fir;
   f->c = c; f->ntaps = ntaps; f->tp = (int)(((ntaps + 7) / 8) * 8); f->mode = mode;
   f->d_taps = f->d_hist = f->d_hist2 = f->d_H = f->d_tw = nullptr; f->nfft = nfft;
-  void* p;
-  std::vector<float2> h(f->tp, make_float2(0.f, 0.f));
-  for (size_t i = 0; i < ntaps; ++i) h[i] = make_float2(taps_host[i].re, taps_host[i].im);
-  TRY(dev_alloc(c, f->tp * sizeof(float2), &p)); f->d_taps = (float2*)p;
-  CK(cudaMemcpyAsync(f->d_taps, h.data(), f->tp * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
-  TRY(dev_alloc(c, f->tp * sizeof(float2), &p)); f->d_hist = (float2*)p;
-  TRY(dev_alloc(c, f->tp * sizeof(float2), &p)); f->d_hist2 = (float2*)p;
-  CK(cudaMemsetAsync(f->d_hist, 0, f->tp * sizeof(float2), c->stream));
-  CK(cudaMemsetAsync(f->d_hist2, 0, f->tp * sizeof(float2), c->stream));
-  if (mode == AE_FIR_OVERLAP_SAVE) {
-    TRY(get_thread_twiddles(c, nfft, &f->d_tw));
-    std::vector<float2> hp(nfft, make_float2(0.f, 0.f));
-    for (size_t i = 0; i < ntaps; ++i) hp[i] = h[i];
-    TRY(dev_alloc(c, nfft * sizeof(float2), &p)); f->d_H = (float2*)p;
-    CK(cudaMemcpyAsync(f->d_H, hp.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
-    // H = DFT(h) / nfft  (the 1/nfft of the forward/inverse round trip is folded in here)
-    launch_fft_pow2(f->d_H, f->d_H, nfft, 1, f->d_tw, false, true, 1.0f / (float)nfft, c->stream);
-    CKL(1);
-  }
-  CK(cudaStreamSynchronize(c->stream));
+  auto build = [&]() -> ae_status {
+    void* p;
+    std::vector<float2> h(f->tp, make_float2(0.f, 0.f));
+    for (size_t i = 0; i < ntaps; ++i) h[i] = make_float2(taps_host[i].re, taps_host[i].im);
+    TRY(dev_alloc(c, f->tp * sizeof(float2), &p)); f->d_taps = (float2*)p;
+    CK(cudaMemcpyAsync(f->d_taps, h.data(), f->tp * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+    TRY(dev_alloc(c, f->tp * sizeof(float2), &p)); f->d_hist = (float2*)p;
+    TRY(dev_alloc(c, f->tp * sizeof(float2), &p)); f->d_hist2 = (float2*)p;
+    CK(cudaMemsetAsync(f->d_hist, 0, f->tp * sizeof(float2), c->stream));
+    CK(cudaMemsetAsync(f->d_hist2, 0, f->tp * sizeof(float2), c->stream));
+    if (mode == AE_FIR_OVERLAP_SAVE) {
+      TRY(get_thread_twiddles(c, nfft, &f->d_tw));
+      std::vector<float2> hp(nfft, make_float2(0.f, 0.f));
+      for (size_t i = 0; i < ntaps; ++i) hp[i] = h[i];
+      TRY(dev_alloc(c, nfft * sizeof(float2), &p)); f->d_H = (float2*)p;
+      CK(cudaMemcpyAsync(f->d_H, hp.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+      // H = DFT(h) / nfft  (the 1/nfft of the forward/inverse round trip is folded in here)
+      launch_fft_pow2(f->d_H, f->d_H, nfft, 1, f->d_tw, false, true, 1.0f / (float)nfft, c->stream);
+      CKL(1);
+    }
+    CK(cudaStreamSynchronize(c->stream));   // also keeps the host staging vectors alive until the copies are done
+    return AE_OK;
+  };
+  const ae_status st = build();
+  if (st != AE_OK) { ae_fir_destroy(f); return st; }
   *out = f;
   return AE_OK;
 }
@@ -952,6 +957,10 @@ ae_status ae_fir_destroy(ae_fir* f) {
   return AE_OK;
 }
 size_t ae_fir_ntaps(const ae_fir* f) { return f ? f->ntaps : 0; }
+size_t ae_fir_block_hop(const ae_fir* f) {
+  if (!f) return 0;
+  return f->mode == AE_FIR_OVERLAP_SAVE ? f->nfft - f->ntaps + 1 : 1;
+}
 ae_status ae_fir_reset(ae_fir* f) {
   if (!f) return fail(AE_EARG, "null");
   cudaSetDevice(f->c->dev);

@@ -315,11 +315,17 @@ AE_X2_DEV void x2_second_stage(cx2 (&v)[16], float2 (&y)[32], float2* ex, const 
   } else {
     static_for<0, 16>([&](auto cc) {
       constexpr int c0 = decltype(cc)::value;
-      float2 o = make_float2(v[c0].re.y, v[c0].im.y);
-      if constexpr (c0 == 8) o = mul_mi<INV>(o);
-      else if constexpr (c0 != 0) o = mul_w<INV>(o, x2_c32(c0), x2_s32(c0));
-      y[c0] = make_float2(v[c0].re.x + o.x, v[c0].im.x + o.y);
-      y[c0 + 16] = make_float2(v[c0].re.x - o.x, v[c0].im.x - o.y);
+      const float2 ev = make_float2(v[c0].re.x, v[c0].im.x), od = make_float2(v[c0].re.y, v[c0].im.y);
+      if constexpr (c0 == 0 || c0 == 8) {
+        const float2 o = c0 == 0 ? od : mul_mi<INV>(od);
+        y[c0] = make_float2(ev.x + o.x, ev.y + o.y);
+        y[c0 + 16] = make_float2(ev.x - o.x, ev.y - o.y);
+      } else {
+        // y+ = E + W O as two FMA chains, y- = 2 E - y+: 6 operations instead of 8
+        constexpr float c = x2_c32(c0), sn = INV ? -x2_s32(c0) : x2_s32(c0);   // W = c - i sn
+        y[c0] = make_float2(fmaf(od.x, c, fmaf(od.y, sn, ev.x)), fmaf(od.y, c, fmaf(-od.x, sn, ev.y)));
+        y[c0 + 16] = make_float2(fmaf(2.0f, ev.x, -y[c0].x), fmaf(2.0f, ev.y, -y[c0].y));
+      }
     });
   }
 }
@@ -334,12 +340,18 @@ AE_X2_DEV void x2_stage1(cx2 (&v)[16], const float2* __restrict__ src, const flo
 #pragma unroll
   for (int m = 0; m < 16; ++m) {
     const int s = t + m * T;
-    float2 a = src[s], b = src[s + N / 2];
+    const float2 a = src[s], b = src[s + N / 2];
+    float2 e, d;
     if (WIN) {
-      a = cx_mul(a, win[s]);
-      b = cx_mul(b, win[s + N / 2]);
+      // e = a wa + b wb, d = a wa - b wb = 2 (a wa) - e: 10 FMA-pipe operations instead of 12
+      const float2 wa = win[s], wb = win[s + N / 2];
+      const float2 pa = cx_mul(a, wa);
+      e = make_float2(fmaf(b.x, wb.x, fmaf(-b.y, wb.y, pa.x)), fmaf(b.x, wb.y, fmaf(b.y, wb.x, pa.y)));
+      d = make_float2(fmaf(2.0f, pa.x, -e.x), fmaf(2.0f, pa.y, -e.y));
+    } else {
+      e = make_float2(a.x + b.x, a.y + b.y);
+      d = make_float2(a.x - b.x, a.y - b.y);
     }
-    const float2 e = make_float2(a.x + b.x, a.y + b.y), d = make_float2(a.x - b.x, a.y - b.y);
     const float2 o = mul_tw<INV>(d, LEAN ? s1tab[s] : tw.s1[m]);
     v[m] = cx2{make_float2(e.x, o.x), make_float2(e.y, o.y)};
   }

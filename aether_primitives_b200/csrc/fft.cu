@@ -358,6 +358,11 @@ __device__ __forceinline__ unsigned gen_pad(unsigned i) { return i + (i >> 5); }
 
 // forward DFT of odd prime length P on registers.  root[r] = exp(-2 pi i r / P), r = 1..(P-1)/2:
 //   X[q], X[P-q] = x0 + sum_r cos(2 pi r q / P) (x_r + x_{P-r})  -/+  i sum_r sin(2 pi r q / P) (x_r - x_{P-r})
+// The cosine sum is evaluated in the DC-exact form: with a_r = x_r + x_{P-r} and sum_r cos(2 pi r q/P) = -1/2,
+//   x0 + sum_r c_rq a_r = (x0 - a_1/2) + sum_{r>=2} c_rq (a_r - a_1),
+// so a CONSTANT input gives exactly zero in every bin but the first, as radix-2/4/8 butterflies do.  The
+// reference's own FFT tests (src/vecops.rs:445-463: N = 100, constant input, SN round trip, assert_evm! at -80,
+// i.e. equality to the bit) rely on exactly that; the plain sum leaves ~1e-7 in the second radix-5 pass.
 template <int P>
 __device__ __forceinline__ void odd_dft(float2 (&v)[P], const float2 (&root)[(P - 1) / 2 + 1]) {
   constexpr int H = (P - 1) / 2;
@@ -367,17 +372,21 @@ __device__ __forceinline__ void odd_dft(float2 (&v)[P], const float2 (&root)[(P 
   float2 y0 = v[0];
 #pragma unroll
   for (int r = 1; r <= H; ++r) y0 = cx_add(y0, a[r]);
+  const float2 base = make_float2(fmaf(-0.5f, a[1].x, v[0].x), fmaf(-0.5f, a[1].y, v[0].y));   // x0 - a_1/2 (exact halving)
+  float2 da[H + 1];
+#pragma unroll
+  for (int r = 2; r <= H; ++r) da[r] = cx_sub(a[r], a[1]);
   float2 o[P];
   o[0] = y0;
 #pragma unroll
   for (int q = 1; q <= H; ++q) {
-    float2 e = v[0], f = make_float2(0.0f, 0.0f);
+    float2 e = base, f = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int r = 1; r <= H; ++r) {
       const int idx = (r * q) % P;                       // compile-time after unrolling
       const float c = idx <= H ? root[idx].x : root[P - idx].x;
       const float sn = idx <= H ? -root[idx].y : root[P - idx].y;   // sin(2 pi idx / P)
-      e.x = fmaf(c, a[r].x, e.x); e.y = fmaf(c, a[r].y, e.y);
+      if (r >= 2) { e.x = fmaf(c, da[r].x, e.x); e.y = fmaf(c, da[r].y, e.y); }
       f.x = fmaf(sn, b[r].x, f.x); f.y = fmaf(sn, b[r].y, f.y);
     }
     o[q] = make_float2(e.x + f.y, e.y - f.x);            // e - i f

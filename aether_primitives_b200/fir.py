@@ -30,6 +30,11 @@ class Fir:
     def ntaps(self) -> int:
         return int(lib().ae_fir_ntaps(self._h))
 
+    def block_hop(self) -> int:
+        """outputs per overlap-save segment (1 for the direct form): shard starts that are multiples of it
+        reproduce the unsharded stream bit for bit (see sharding.ShardedFir)"""
+        return int(lib().ae_fir_block_hop(self._h))
+
     def reset(self) -> None:
         call("ae_fir_reset", self._h)
 

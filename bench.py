@@ -30,7 +30,7 @@ if ROOT not in sys.path:
 FFT_LEN = 1024
 NTAPS = 64
 ALG_BYTES_PER_SAMPLE = 10.0   # 8 B cf32 in + 2 B bits out (SURVEY §8d headline row)
-FLOP_PER_SAMPLE = 2 * 50 + 6 + 16  # two 1024-pt FFTs + window multiply + triangular fix-up
+FLOP_PER_SAMPLE = 2 * 50 + 6 + 16  # two 1024-pt FFTs + window multiply + triangular fix-up (nominal 5 N log2 N count)
 METRIC = "cf32 Gsamples/s, FFT->FIR->QPSK-demod chain (1024-pt fwd FFT, 64-tap FIR, hard demod)"
 
 
@@ -212,10 +212,13 @@ def timed(torch, fn, steps: int, warmup: int, barrier=None):
     return e0.elapsed_time(e1) / 1e3
 
 
-def extras(torch, ae, d_in, frames, hbm_peak, steps=5, warmup=3):
-    """Stand-alone kernels of the other BASELINE configs, device-timed, each with its algorithmic
-    bytes and fraction of the measured HBM peak.  Reported for information under "extra"."""
+def extras(torch, ae, d_in, frames, hbm_peak, steps=5, warmup=3, rank=0, world=1):
+    """Stand-alone kernels of the other BASELINE configs, device-timed on THIS rank's GPU, each with its
+    algorithmic bytes and fraction of the measured HBM peak.  Reported under "extra"; for N > 1 every rank
+    runs them on its own shard (weak scaling) and run_ours() combines the ranks (max time, summed units).
+    Config 3 is the exception: one 2^28-sample stream cut into `world` shards with a (T-1)-sample halo."""
     from aether_primitives_b200 import fir as F
+    from aether_primitives_b200.sharding import ShardedFir
     from aether_primitives_b200.stats import DeviceStats
 
     out = {}
@@ -258,6 +261,18 @@ def extras(torch, ae, d_in, frames, hbm_peak, steps=5, warmup=3):
                        ("fir1024_overlap_save", F.Fir(make_taps(1024), F.OVERLAP_SAVE))):
         t = timed(torch, lambda: filt.filter(a, b), steps, warmup) / steps
         rec(name, 16.0 * m, t, m, "samples")
+    # config 3 across GPUs: ONE stream of 2^28 samples, rank r filters [r n/R - halo, (r+1) n/R) and keeps its n/R outputs
+    # (strong scaling; "units" are this rank's outputs, so the combined line is the rate of the whole stream)
+    total = 1 << 28
+    for name, tp in (("fir64_stream_sharded", 64), ("fir1024_stream_sharded", 1024)):
+        sh = ShardedFir(make_taps(tp), total, rank, world, F.OVERLAP_SAVE)
+        lo_in, hi = sh.input_range()
+        xs = d_in.view(0, hi - lo_in)          # synthetic stream: any N(0,1) samples of the right length
+        t = timed(torch, lambda: sh.filter(xs), steps, warmup) / steps
+        rec(name, 16.0 * (sh.hi - sh.lo), t, sh.hi - sh.lo, "samples")
+        out[name]["halo_samples"] = sh.halo + (hi - sh.hi)
+        out[name]["strong_scaling_total_samples"] = total
+        del sh
     # config 1: modem loop-back at 1M symbols (launch-bound) and 2^28 symbols
     qpsk = ae.modulation.qpsk()
     g = ae.noise.new(0.01, 815)
@@ -468,7 +483,27 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         h2d = 3 * 8 * ne / (c0.elapsed_time(c1) / 1e3) / 1e9
         e2e["h2d_copy_GB/s"] = h2d
         e2e["frac_of_h2d_copy"] = (8 * ne * e_steps / e_secs / 1e9) / h2d
-        del d_tmp
+        # yard-stick of the WHOLE job: every rank at once (same barrier), both directions at once (the step moves 8 B in
+        # and 2 B out per sample), bare cudaMemcpyAsync on two streams: what the host fabric gives N concurrent ranks
+        d_out_tmp = torch.empty(2 * ne, dtype=torch.uint8, device="cuda")
+        h_out2 = torch.empty(2 * ne, dtype=torch.uint8).pin_memory()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        barrier()
+        torch.cuda.synchronize()
+        tw0 = time.perf_counter()
+        for _ in range(3):
+            with torch.cuda.stream(s_in):
+                d_tmp.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_out2.copy_(d_out_tmp, non_blocking=True)
+        torch.cuda.synchronize()
+        ty = torch.tensor([time.perf_counter() - tw0], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(ty, op=dist.ReduceOp.MAX)
+        yard = world * ne * 3 / float(ty.item()) / 1e9          # Gsamples/s the bare copies of all ranks sustain together
+        e2e["concurrent_copy_yardstick_Gsamples/s"] = yard
+        e2e["frac_of_concurrent_yardstick"] = e2e["value"] / yard
+        del d_tmp, d_out_tmp, h_out2
         del h_in, h_out
         try:
             os.sched_setaffinity(0, affinity0)       # the CPU baseline below uses every host core
@@ -482,7 +517,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     config5 = None
     try:
         from aether_primitives_b200.sharding import frame_range
-        from aether_primitives_b200.stats import DeviceStats, allreduce, evm_db
+        from aether_primitives_b200.stats import Comm, DeviceStats, evm_db
 
         total_frames = (1 << 18) * world                      # 2^18 frames per GPU
         f0, f1 = frame_range(total_frames, rank, world)
@@ -492,26 +527,53 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             ofdm()
         st.zero()
         t5 = timed(torch, ofdm, 5, 0, barrier) / 5
-        local = st.read()
         tt5 = torch.tensor([t5], dtype=torch.float64, device="cuda")
         if dist:
             dist.all_reduce(tt5, op=dist.ReduceOp.MAX)
-        red = allreduce(local)
+            # the path's only collective, through the C ABI: ae_comm_init_rank + ae_stats_allreduce (NCCL inside the
+            # library; torch.distributed only carried the 128-byte id to the ranks)
+            comm = Comm.from_torch_distributed()
+            st.allreduce(comm)
+            red = st.read()
+            comm.close()
+        else:
+            red = st.read()
         config5 = {"workload": "mseq -> QPSK -> 2048-pt bwd FFT(SN) -> AWGN -> fwd FFT(SN) -> demod -> BER/EVM", "frames_total": total_frames,
                    "Gsymbols/s": total_frames * 2048 / float(tt5.item()) / 1e9, "ms": float(tt5.item()) * 1e3,
                    "bit_errors": red["bit_errors"], "n_bits": red["n_bits"], "ber": red["bit_errors"] / max(1, red["n_bits"]),
-                   "evm_db": evm_db(red["err_pow"], red["ref_pow"]), "collective": "all_reduce(sum) of 4 counters, %s" % ("nccl" if dist else "single rank")}
+                   "evm_db": evm_db(red["err_pow"], red["ref_pow"]), "collective": "ae_stats_allreduce (ncclAllReduce inside libaether_b200.so), %d ranks" % world if dist else "single rank"}
     except Exception as ex:
         config5 = {"error": repr(ex)}
 
     extra = None
     cpu = None
+    if not args.no_extras:
+        try:
+            extra = extras(torch, ae, d_in, frames, hbm_peak, rank=rank, world=world)
+        except Exception as ex:  # extras never invalidate the headline line
+            extra = {"error": repr(ex)}
+        if dist:
+            # every named shape at N GPUs: slowest rank's time, units summed over ranks; frac_hbm stays per GPU
+            gathered = [None] * world
+            dist.all_gather_object(gathered, extra)
+            if rank == 0 and all(isinstance(g, dict) and "error" not in g for g in gathered):
+                comb = {}
+                for name, e0 in gathered[0].items():
+                    ms = max(g[name]["ms"] for g in gathered)
+                    row = {"ms": ms, "n_gpus": world}
+                    for k in e0:
+                        if k.startswith("G") and k.endswith("/s"):
+                            units = sum(g[name][k] * g[name]["ms"] for g in gathered)     # G-units x ms, per rank
+                            row[k] = units / ms
+                            row[k + "_per_gpu"] = row[k] / world
+                    if "frac_hbm" in e0:
+                        row["frac_hbm_per_gpu"] = min(g[name]["frac_hbm"] * g[name]["ms"] / ms for g in gathered)
+                    for k in ("halo_samples", "strong_scaling_total_samples", "bytes_note"):
+                        if k in e0:
+                            row[k] = e0[k]
+                    comb[name] = row
+                extra = comb
     if rank == 0 and world == 1:
-        if not args.no_extras:
-            try:
-                extra = extras(torch, ae, d_in, frames, hbm_peak)
-            except Exception as ex:  # extras never invalidate the headline line
-                extra = {"error": repr(ex)}
         if not args.no_cpu:
             threads = os.cpu_count() or 1
             gs, ms, cf = cpu_chain_rate(10.0, threads)
@@ -538,12 +600,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "config": {"workload": "fft1024_fwd_SN -> fir64 -> qpsk_demod (BASELINE headline chain)", "fft_len": FFT_LEN, "ntaps": NTAPS,
                        "frames_per_gpu": frames, "samples_per_gpu": n, "compat": "reference", "parallelism": "frames sharded, dp%d" % world,
                        "l2_policy": "inputs larger than L2 (%.1f GiB in, %.1f GiB out per step)" % (8 * n / 2**30, 2 * n / 2**30)},
-            "roofline": {"bound": "hbm", "kernel": "chain_fused_kernel<1024>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "chain_x2_kernel<1024> (K14b)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write per sample from profiles/chain_traffic.json x samples per launch",
                          "peak_source": peak_src,
                          "alg_bytes_per_sample": ALG_BYTES_PER_SAMPLE, "kernel_ms": kernel_s * 1e3,
-                         "limiter": "not HBM: instruction issue 76 % and L1/shared data pipe 77 % busy (ncu, profiles/r1_chain_v8_ncu_summary.txt); "
-                                    "two 1024-pt FFTs + fix-up + decisions = ~107 instructions per sample (DESIGN.md 5.2)",
+                         "limiter": "not HBM: instruction dispatch.  Packed FP32 (FFMA2/FADD2), 16-lane ALU and LSU instructions hold the "
+                                    "sub-partition's dispatch port for two cycles each; the sum of the SASS stall fields of one frame "
+                                    "(~3300 cycles per warp-frame) is the frame time within 10 % (DESIGN.md 5.2, profiles/r2_*)",
                          "fp32_TFLOP/s_nominal": FLOP_PER_SAMPLE * n / kernel_s / 1e12},
             "e2e": e2e, "gpu_launches": launches, "warmup_launches": l_warm, "clocks": clocks,
             "checksum_ones": int(ones.item()),

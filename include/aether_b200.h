@@ -141,6 +141,10 @@ enum { AE_FIR_AUTO = 0, AE_FIR_DIRECT = 1, AE_FIR_OVERLAP_SAVE = 2 };   /* AUTO 
 ae_status ae_fir_create(const ae_cf32* taps_host, size_t ntaps, int mode, ae_fir** out); /* Fir::new :14 */
 ae_status ae_fir_destroy(ae_fir* f);
 size_t    ae_fir_ntaps(const ae_fir* f);
+/* Outputs per overlap-save segment (FFT block length - ntaps + 1; 1 for the direct form).  A stream that is cut into
+ * shards whose first sample is a multiple of this hop is filtered with exactly the segment boundaries of the whole
+ * stream, so shard results are bit-identical to the unsharded run (multi-GPU FIR). */
+size_t    ae_fir_block_hop(const ae_fir* fir);
 ae_status ae_fir_reset(ae_fir* f);                            /* zero the carried history */
 /* y[n] = sum_k h[k] x[n-k]; out.len == in.len.  frame_len = 0: one stream, history carried
  * across calls (T-1 samples); frame_len > 0: zero state at the start of every frame. */

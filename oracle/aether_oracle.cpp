@@ -236,6 +236,37 @@ void fft_rec(const FftPlan<T>& pl, const std::complex<T>* in, std::complex<T>* o
       out[k + 2 * m] = s0 - s2;
       out[k + 3 * m] = s1 - js3;
     }
+  } else if (p == 3 || p == 5 || p == 7 || p == 11 || p == 13) {
+    // rustfft's small odd butterflies (Butterfly3 / Butterfly5 / ... of rustfft ^3.0, restated from its published
+    // algorithm; the crate is not vendored): with a_r = x_r + x_{p-r}, b_r = x_r - x_{p-r},
+    //   X[q], X[p-q] = (x0 + sum_r Re(w^(rq)) a_r)  +/-  i-rotated (sum_r Im(w^(rq)) b_r),
+    // every product and sum rounded separately, left to right (this file is built with -ffp-contract=off).
+    // For a constant input the cosine sum cancels to exactly 0 in f32 (cos(4 pi/5) == -(1/2 + cos(2 pi/5)) holds for
+    // the rounded constants too), which is what lets the reference's N = 100 round-trip tests
+    // (src/vecops.rs:445-463) pass assert_evm! at -80 = equality to the bit.
+    std::complex<T>* t = scratch;  // p entries
+    const size_t wp = pl.n / p;    // W_p^q = tw[q*wp]
+    const size_t hh = (p - 1) / 2;
+    std::complex<T> a[7], b[7], o[13];
+    for (size_t k = 0; k < m; ++k) {
+      for (size_t r = 0; r < p; ++r) t[r] = cmul(out[k + r * m], W(r * k * tws));
+      std::complex<T> sum = t[0];
+      for (size_t r = 1; r <= hh; ++r) { a[r] = t[r] + t[p - r]; b[r] = t[r] - t[p - r]; sum += a[r]; }
+      o[0] = sum;
+      for (size_t q = 1; q <= hh; ++q) {
+        T ere = t[0].real(), eim = t[0].imag(), fre = 0, fim = 0;
+        for (size_t r = 1; r <= hh; ++r) {
+          const std::complex<T> w = W(((r * q) % p) * wp);
+          ere = ere + w.real() * a[r].real();
+          eim = eim + w.real() * a[r].imag();
+          fre = fre + w.imag() * b[r].imag();
+          fim = fim + w.imag() * b[r].real();
+        }
+        o[q] = std::complex<T>(ere - fre, eim + fim);
+        o[p - q] = std::complex<T>(ere + fre, eim - fim);
+      }
+      for (size_t q = 0; q < p; ++q) out[k + q * m] = o[q];
+    }
   } else {
     std::complex<T>* t = scratch;  // p entries
     const size_t wp = pl.n / p;    // W_p^q = tw[q*wp]

@@ -75,9 +75,11 @@ def test_fft_roundtrip_100():
         f = o.cfft(v, c["n"], bwd=False, scale_kind=o.SCALE_SN, compat=compat)
         b = o.cfft(f, c["n"], bwd=True, scale_kind=o.SCALE_SN, compat=compat)
         assert evm_db(b, v) < -120.0
-        # the literal macro at -80 "dB" demands |err| <= 1e-8*|ref|, i.e. bit equality
-        worst = o.evm_macro_worst_db(b, v)
-        assert worst < -60.0 or worst == -np.inf
+        # the reference's own assertion (src/vecops.rs:445-463), literally: assert_evm!(c, v) at the default -80,
+        # i.e. |err| <= 1e-8 |ref| = equality to the bit.  It holds because the odd butterflies (rustfft's form,
+        # restated in the oracle) give exact zeros for a constant input.
+        assert o.assert_evm(b, v, -80.0)[0] == o.OK
+        assert np.array_equal(b.view(np.uint32), v.view(np.uint32))
 
 
 def test_fft_doctest_128():
