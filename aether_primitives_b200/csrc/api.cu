@@ -11,6 +11,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -62,6 +63,7 @@ ae_status fail(ae_status st, const std::string& msg) {
   } while (0)
 #define CKL(n)                                                                                \
   do {                                                                                        \
+    if (const char* u__ = ae::take_unsupported_launch()) return fail(AE_EARG, std::string("no kernel for this shape: ") + u__); \
     g_launches += (n);                                                                        \
     cudaError_t e__ = cudaGetLastError();                                                     \
     if (e__ != cudaSuccess) return fail(AE_ECUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e__)); \
@@ -71,6 +73,34 @@ ae_status fail(ae_status st, const std::string& msg) {
     ae_status s__ = (expr);              \
     if (s__ != AE_OK) return s__;        \
   } while (0)
+
+}  // namespace
+namespace ae {
+namespace {
+thread_local const char* t_unsupported = nullptr;
+struct ResKey { const void* k; int dev; int threads; size_t smem; bool operator<(const ResKey& o) const { return std::tie(k, dev, threads, smem) < std::tie(o.k, o.dev, o.threads, o.smem); } };
+std::map<ResKey, size_t> g_resident;
+std::mutex g_resident_mu;
+}  // namespace
+void note_unsupported_launch(const char* what) { t_unsupported = what; }
+const char* take_unsupported_launch() { const char* w = t_unsupported; t_unsupported = nullptr; return w; }
+size_t resident_ctas(const void* kern, int threads, size_t smem) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const ResKey key{kern, dev, threads, smem};
+  std::lock_guard<std::mutex> lk(g_resident_mu);
+  auto it = g_resident.find(key);
+  if (it != g_resident.end()) return it->second;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 1, sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const size_t r = (size_t)sms * per_sm;
+  g_resident[key] = r;
+  return r;
+}
+}  // namespace ae
+namespace {
 
 ae_status get_ctx(Ctx** out) {
   if (t_dev < 0) {

@@ -260,7 +260,7 @@ void launch_chain_fused(const float2* x, uint8_t* bits, size_t nfft, size_t fram
 #define AE_CASE(NN) case NN: launch_chain_n<NN>(x, bits, frames, window, taps, ntaps, tw, inverse, scale, compat, st); break;
     AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096)
 #undef AE_CASE
-    default: break;
+    default: note_unsupported_launch("fused chain: FFT length must be a power of two in 256..4096");
   }
 }
 
@@ -451,12 +451,7 @@ static void launch_ofdm_n(size_t frames, uint64_t first_frame, float noise_scale
   const uint32_t* zj = ofdm_column_table(FftCfg<N>::T, st);
   if (!zj) return;
   auto launch = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 1, dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, smem);
-    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+    const size_t resident = resident_ctas((const void*)kern, LC::THREADS, smem);
     const unsigned grid = (unsigned)(want < resident ? want : resident);
     kern<<<grid, LC::THREADS, smem, st>>>(frames, first_frame, noise_scale, twice, make_philox_keys(seed), tw, zj, compat, tx_bits, rx_bits, stats);
   };
@@ -471,7 +466,7 @@ void launch_ofdm_chain(size_t nfft, size_t frames, uint64_t first_frame, float n
 #define AE_CASE(NN) case NN: launch_ofdm_n<NN>(frames, first_frame, noise_scale, twice, seed, tw, compat, tx_bits, rx_bits, stats, st); break;
     AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096)
 #undef AE_CASE
-    default: break;
+    default: note_unsupported_launch("OFDM chain: FFT length must be a power of two in 512..4096");
   }
 }
 

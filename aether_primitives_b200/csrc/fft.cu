@@ -129,12 +129,7 @@ static void launch_pow2_n(const float2* in, float2* out, size_t frames, const fl
   const bool staged = ((uintptr_t)in % 16) == 0 && use_tma && N >= 64 && N <= 2048;
   auto launch = [&](auto kern, bool stg) {
     const size_t smem = LC::smem(stg);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 1, dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, smem);
-    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);  // grid = SM count x resident CTAs
+    const size_t resident = resident_ctas((const void*)kern, LC::THREADS, smem);  // grid = SM count x resident CTAs
     const unsigned grid = (unsigned)(want < resident ? want : resident);
     kern<<<grid, LC::THREADS, smem, st>>>(in, out, tw, frames, scale, do_scale);
   };
@@ -186,7 +181,7 @@ void launch_fft_pow2(const float2* in, float2* out, size_t n, size_t frames, con
     AE_CASE(16) AE_CASE(32) AE_CASE(64) AE_CASE(128) AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048)
     AE_CASE(4096) AE_CASE(8192) AE_CASE(16384)
 #undef AE_CASE
-    default: break;
+    default: note_unsupported_launch("power-of-two FFT kernel: length must be 16..16384");
   }
 }
 
@@ -268,7 +263,7 @@ static void launch_col_n(const float2* in, float2* out, const float2* tw, const 
                          size_t frames, size_t frame_elems, bool inverse, bool do_scale, float scale, cudaStream_t st) {
   using LC = ColLaunch<N1>;
   auto launch = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
+    (void)resident_ctas((const void*)kern, LC::THREADS, LC::SMEM);   // shared-memory opt-in, once per device
     for (size_t f0 = 0; f0 < frames; f0 += 32768) {
       const size_t fc = frames - f0 < 32768 ? frames - f0 : 32768;
       const dim3 grid((unsigned)(ncols / LC::CT), (unsigned)fc);
@@ -576,12 +571,7 @@ void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n
     }
     const unsigned slots = gen_slots(n);
     const size_t smem = 2 * ((size_t)slots * n + (slots * n) / 32 + 2) * sizeof(float2);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(fft_generic_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 1, dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_generic_smem_kernel, 256, smem);
-    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+    const size_t resident = resident_ctas((const void*)fft_generic_smem_kernel, 256, smem);
     const size_t want = (frames + slots - 1) / slots;
     fft_generic_smem_kernel<<<(unsigned)(want < resident ? want : resident), 256, smem, st>>>(in, out, tw, (unsigned)n, frames, slots, rad,
                                                                                           inverse, do_scale, scale);

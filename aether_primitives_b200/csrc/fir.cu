@@ -276,7 +276,7 @@ static void launch_os_n(const float2* x, float2* y, size_t n, const float2* H, c
   } else {
     n_segs = (n + L - 1) / L;
   }
-  if (LC::SMEM > 48 * 1024) cudaFuncSetAttribute(fir_os_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
+  (void)resident_ctas((const void*)fir_os_kernel<NF>, LC::THREADS, LC::SMEM);   // shared-memory opt-in, once per device
   const unsigned grid = (unsigned)((n_segs + LC::F - 1) / LC::F);
   fir_os_kernel<NF><<<grid, LC::THREADS, LC::SMEM, st>>>(x, y, n, H, tw, (int)ntaps, hist_len, history, frame_len, segs_per_frame, n_segs);
 }
@@ -290,7 +290,7 @@ void launch_fir_overlap_save(const float2* x, float2* y, size_t n, const float2*
 #define AE_CASE(NN) case NN: launch_os_n<NN>(x, y, n, H, tw, ntaps, history, hist_len, frame_len, st); break;
     AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096) AE_CASE(8192) AE_CASE(16384)
 #undef AE_CASE
-    default: break;
+    default: note_unsupported_launch("overlap-save FIR: block length must be a power of two in 256..16384");
   }
 }
 

@@ -8,6 +8,15 @@
 
 namespace ae {
 
+// Resident CTAs (SM count x CTAs per SM) of `kern` at (threads, dynamic shared memory) on the current device,
+// including the opt-in for more than 48 KB of dynamic shared memory.  Queried once per (kernel, device, size): the
+// reference API is one frame per call, where three driver calls per launch would be most of the cost.
+size_t resident_ctas(const void* kern, int threads, size_t smem);
+// Launchers are void; an unsupported length / shape is recorded here and turned into AE_EARG by the next CKL() in
+// api.cu instead of silently launching nothing.
+void note_unsupported_launch(const char* what);
+const char* take_unsupported_launch();
+
 // ---- K1 fused VecOps tape -------------------------------------------------------------------
 enum TapeOpcode : int { OP_SCALE = 0, OP_MUL, OP_DIV, OP_ADD, OP_SUB, OP_CONJ, OP_MIRROR, OP_CLONE, OP_ZERO };
 constexpr int kMaxTape = 16;

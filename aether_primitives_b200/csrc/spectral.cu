@@ -83,12 +83,7 @@ static void launch_spec_n(const float2* in, size_t n_samples, float* levels, con
   using LC = SpecLaunch<N, 256>;
   const size_t want = (frames + LC::F - 1) / LC::F;
   auto launch = [&](auto kern) {
-    if (LC::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
-    int per_sm = 1, dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, LC::SMEM);
-    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+    const size_t resident = resident_ctas((const void*)kern, LC::THREADS, LC::SMEM);
     kern<<<(unsigned)(want < resident ? want : resident), LC::THREADS, LC::SMEM, st>>>(in, n_samples, levels, tw, frames, scale, use_db);
   };
   if (inverse) launch(spectrogram_kernel<N, true>);
@@ -102,7 +97,7 @@ void launch_spectrogram(const float2* in, size_t n_samples, float* levels, size_
 #define AE_CASE(NN) case NN: launch_spec_n<NN>(in, n_samples, levels, tw, frames, inverse, scale, use_db, st); break;
     AE_CASE(16) AE_CASE(32) AE_CASE(64) AE_CASE(128) AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096) AE_CASE(8192)
 #undef AE_CASE
-    default: break;
+    default: note_unsupported_launch("spectral kernels: FFT length must be a power of two in 64..4096");
   }
 }
 bool spectral_supported(size_t n) { return n >= 16 && n <= 8192 && (n & (n - 1)) == 0; }
@@ -153,12 +148,7 @@ static void launch_corr_n(float2* data, const float2* sig, const float2* tw, siz
   using LC = SpecLaunch<N, 128>;
   const size_t want = (frames + LC::F - 1) / LC::F;
   auto launch = [&](auto kern) {
-    if (LC::SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC::SMEM);
-    int per_sm = 1, dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LC::THREADS, LC::SMEM);
-    const size_t resident = (size_t)sms * (per_sm > 0 ? per_sm : 1);
+    const size_t resident = resident_ctas((const void*)kern, LC::THREADS, LC::SMEM);
     kern<<<(unsigned)(want < resident ? want : resident), LC::THREADS, LC::SMEM, st>>>(data, sig, tw, frames, scale, do_scale);
   };
   if (fwd_inverse) launch(correlate_kernel<N, true>);
@@ -172,7 +162,7 @@ void launch_correlate(float2* data, const float2* sig, size_t n, size_t frames, 
 #define AE_CASE(NN) case NN: launch_corr_n<NN>(data, sig, tw, frames, fwd_inverse, scale, do_scale, st); break;
     AE_CASE(16) AE_CASE(32) AE_CASE(64) AE_CASE(128) AE_CASE(256) AE_CASE(512) AE_CASE(1024) AE_CASE(2048) AE_CASE(4096) AE_CASE(8192)
 #undef AE_CASE
-    default: break;
+    default: note_unsupported_launch("spectral kernels: FFT length must be a power of two in 64..4096");
   }
 }
 
