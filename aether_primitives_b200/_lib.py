@@ -157,6 +157,10 @@ _SIGS = {
     "ae_pipe_recv": (None, [_P, C.POINTER(_P)]),
     "ae_pipe_in_flight": (_SZ, [_P]),
     "ae_pipe_report": (None, [_P, C.POINTER(PipeStage), _I]),
+    "ae_graph_begin": (None, []),
+    "ae_graph_end": (None, [C.POINTER(_P)]),
+    "ae_graph_launch": (None, [_P]),
+    "ae_graph_destroy": (None, [_P]),
     "ae_chain_exec_unfused": (None, [_P, _P, _P, _P]),
     "ae_ofdm_chain": (None, [_SZ, _SZ, _U64, _F, _U64, _I, _P, _P, _P]),
     "ae_f32_alloc": (None, [_SZ, C.POINTER(_P)]),

@@ -924,6 +924,7 @@ struct ae_fir {
   size_t nfft;
   float2* d_H;
   float2* d_tw;
+  float2* d_x2tw;  // K4b (1024-point blocks): per-thread twiddle rows of the packed transform, else null
 };
 
 extern "C" {
@@ -950,7 +951,7 @@ ae_status ae_fir_create(const ae_cf32* taps_host, size_t ntaps, int mode, ae_fir
   if (mode == AE_FIR_OVERLAP_SAVE && !os_ok) return fail(AE_EARG, "overlap-save FIR supports at most 4096 taps");
   ae_fir* f = new ae_fir;
   f->c = c; f->ntaps = ntaps; f->tp = (int)(((ntaps + 7) / 8) * 8); f->mode = mode;
-  f->d_taps = f->d_hist = f->d_hist2 = f->d_H = f->d_tw = nullptr; f->nfft = nfft;
+  f->d_taps = f->d_hist = f->d_hist2 = f->d_H = f->d_tw = f->d_x2tw = nullptr; f->nfft = nfft;
   auto build = [&]() -> ae_status {
     void* p;
     std::vector<float2> h(f->tp, make_float2(0.f, 0.f));
@@ -970,6 +971,14 @@ ae_status ae_fir_create(const ae_cf32* taps_host, size_t ntaps, int mode, ae_fir
       // H = DFT(h) / nfft  (the 1/nfft of the forward/inverse round trip is folded in here)
       launch_fft_pow2(f->d_H, f->d_H, nfft, 1, f->d_tw, false, true, 1.0f / (float)nfft, c->stream);
       CKL(1);
+      static const char* os_v1 = getenv("AE_FIR_OS_V1");   // developer switch: K4 (two warps per segment) for 1024-point blocks too
+      if (nfft == 1024 && !os_v1) {
+        std::vector<float2> tw, hi, lo;
+        chain_x2_tables(1024, h.data(), 1, tw, hi, lo);
+        TRY(dev_alloc(c, tw.size() * sizeof(float2), &p)); f->d_x2tw = (float2*)p;
+        CK(cudaMemcpyAsync(f->d_x2tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));   // tw is a local of this block
+      }
     }
     CK(cudaStreamSynchronize(c->stream));   // also keeps the host staging vectors alive until the copies are done
     return AE_OK;
@@ -982,7 +991,7 @@ ae_status ae_fir_create(const ae_cf32* taps_host, size_t ntaps, int mode, ae_fir
 ae_status ae_fir_destroy(ae_fir* f) {
   if (!f) return AE_OK;
   cudaSetDevice(f->c->dev);
-  dev_free(f->c, f->d_taps); dev_free(f->c, f->d_hist); dev_free(f->c, f->d_hist2); dev_free(f->c, f->d_H);
+  dev_free(f->c, f->d_taps); dev_free(f->c, f->d_hist); dev_free(f->c, f->d_hist2); dev_free(f->c, f->d_H); dev_free(f->c, f->d_x2tw);
   delete f;
   return AE_OK;
 }
@@ -1022,6 +1031,7 @@ ae_status ae_fir_exec(ae_fir* f, ae_vec* in, ae_vec* out, size_t frame_len) {
   }
   const float2* hist = frame_len ? nullptr : f->d_hist;
   if (mode == AE_FIR_DIRECT) launch_fir_direct(x, y, n, f->d_taps, f->tp, hist, frame_len, c->sm_count, c->stream);
+  else if (f->d_x2tw) launch_fir_os_x2(x, y, n, f->d_H, f->d_x2tw, f->ntaps, hist, frame_len, c->stream);
   else launch_fir_overlap_save(x, y, n, f->d_H, f->d_tw, f->nfft, f->ntaps, hist, frame_len, c->stream);
   CKL(1);
   if (!frame_len && f->tp > 1) {  // carry the last tp-1 inputs
@@ -1694,29 +1704,76 @@ ae_status ae_chain_exec_host(ae_chain* ch, const ae_cf32* host_in, size_t n_samp
   // order the pipeline after work already queued on the context stream
   cudaEvent_t ev;
   CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CK(cudaEventRecord(ev, c->stream));
-  for (int i = 0; i < 3; ++i) CK(cudaStreamWaitEvent(c->pipe[i], ev, 0));
-  size_t done = 0;
-  int slot = 0;
-  while (done < frames) {
-    const size_t fc = std::min(ch->chunk_frames, frames - done);
-    cudaStream_t st = c->pipe[slot];
-    CK(cudaMemcpyAsync(ch->d_in[slot], host_in + done * ch->n, fc * ch->n * sizeof(float2), cudaMemcpyHostToDevice, st));
-    chain_launch(ch, ch->d_in[slot], ch->d_out[slot], fc, st);
-    CKL(1);
-    CK(cudaMemcpyAsync(host_bits + 2 * done * ch->n, ch->d_out[slot], fc * ch->n * 2, cudaMemcpyDeviceToHost, st));
-    done += fc;
-    slot = (slot + 1) % 3;
-  }
-  for (int i = 0; i < 3; ++i) {
-    CK(cudaEventRecord(ev, c->pipe[i]));
-    CK(cudaStreamWaitEvent(c->stream, ev, 0));
-  }
-  CK(cudaEventDestroy(ev));
-  for (int i = 0; i < 3; ++i) CK(cudaStreamSynchronize(c->pipe[i]));
-  return AE_OK;
+  auto run = [&]() -> ae_status {
+    CK(cudaEventRecord(ev, c->stream));
+    for (int i = 0; i < 3; ++i) CK(cudaStreamWaitEvent(c->pipe[i], ev, 0));
+    size_t done = 0;
+    int slot = 0;
+    while (done < frames) {
+      const size_t fc = std::min(ch->chunk_frames, frames - done);
+      cudaStream_t st = c->pipe[slot];
+      CK(cudaMemcpyAsync(ch->d_in[slot], host_in + done * ch->n, fc * ch->n * sizeof(float2), cudaMemcpyHostToDevice, st));
+      chain_launch(ch, ch->d_in[slot], ch->d_out[slot], fc, st);
+      CKL(1);
+      CK(cudaMemcpyAsync(host_bits + 2 * done * ch->n, ch->d_out[slot], fc * ch->n * 2, cudaMemcpyDeviceToHost, st));
+      done += fc;
+      slot = (slot + 1) % 3;
+    }
+    for (int i = 0; i < 3; ++i) {
+      CK(cudaEventRecord(ev, c->pipe[i]));
+      CK(cudaStreamWaitEvent(c->stream, ev, 0));
+    }
+    for (int i = 0; i < 3; ++i) CK(cudaStreamSynchronize(c->pipe[i]));
+    return AE_OK;
+  };
+  const ae_status st = run();
+  cudaEventDestroy(ev);      // on every path
+  return st;
 }
 
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// CUDA graphs over the context stream (launch-bound shapes)
+// -------------------------------------------------------------------------------------------------
+struct ae_graph {
+  Ctx* c;
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+};
+extern "C" {
+ae_status ae_graph_begin(void) {
+  Ctx* c;
+  TRY(get_ctx(&c));
+  CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+  return AE_OK;
+}
+ae_status ae_graph_end(ae_graph** out) {
+  if (!out) return fail(AE_EARG, "null");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  cudaGraph_t g = nullptr;
+  CK(cudaStreamEndCapture(c->stream, &g));
+  cudaGraphExec_t ex = nullptr;
+  const cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+  if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(AE_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+  *out = new ae_graph{c, g, ex};
+  return AE_OK;
+}
+ae_status ae_graph_launch(ae_graph* g) {
+  if (!g) return fail(AE_EARG, "null");
+  cudaSetDevice(g->c->dev);
+  CK(cudaGraphLaunch(g->exec, g->c->stream));
+  return AE_OK;
+}
+ae_status ae_graph_destroy(ae_graph* g) {
+  if (!g) return AE_OK;
+  cudaSetDevice(g->c->dev);
+  cudaGraphExecDestroy(g->exec);
+  cudaGraphDestroy(g->graph);
+  delete g;
+  return AE_OK;
+}
 }  // extern "C"
 
 // -------------------------------------------------------------------------------------------------

@@ -205,8 +205,16 @@ chain_fused_kernel(const float2* __restrict__ x, uint8_t* __restrict__ bits, siz
   }  // frame loop
 }
 
+// dynamic shared memory of chain_fused_kernel<nfft> (layout above); must stay below the 227 KB opt-in limit
+static size_t chain_smem_bytes(size_t nfft, size_t ntaps, bool staged) {
+  const size_t T = nfft / 16, F = T >= 128 ? 1 : 128 / T;
+  const size_t slot = 2 * (nfft + nfft / 16) + 3 * (size_t)chain_rp((int)ntaps) + (staged ? nfft : 0);
+  return (2 * (size_t)chain_hp((int)ntaps) + F * slot) * sizeof(float2) + F * sizeof(uint64_t);
+}
+constexpr size_t kSmemOptinLimit = 227 * 1024;
 bool chain_fused_supported(size_t nfft, size_t ntaps) {
-  return nfft >= 256 && nfft <= 4096 && (nfft & (nfft - 1)) == 0 && ntaps >= 1 && ntaps <= nfft;
+  return nfft >= 256 && nfft <= 4096 && (nfft & (nfft - 1)) == 0 && ntaps >= 1 && ntaps <= nfft &&
+         chain_smem_bytes(nfft, ntaps, false) <= kSmemOptinLimit;   // else the plan takes the unfused path
 }
 
 template <int N, bool STAGED, class K>
@@ -241,7 +249,7 @@ static void launch_chain_n(const float2* x, uint8_t* bits, size_t frames, const 
                            size_t ntaps, const float2* tw, bool inverse, float scale, int compat, cudaStream_t st) {
   const bool prune = ntaps - 1 <= (size_t)FftCfg<N>::T;
   static const char* no_tma = getenv("AE_CHAIN_NO_TMA");
-  const bool staged = ((uintptr_t)x % 16) == 0 && !no_tma;
+  const bool staged = ((uintptr_t)x % 16) == 0 && !no_tma && chain_smem_bytes(N, ntaps, true) <= kSmemOptinLimit;
 #define AE_GO(I, P, S) launch_chain_kernel<N, S>(chain_fused_kernel<N, I, P, S>, x, bits, frames, window, taps, ntaps, tw, scale, compat, st)
   if (inverse) {
     if (prune) { if (staged) AE_GO(true, true, true); else AE_GO(true, true, false); }

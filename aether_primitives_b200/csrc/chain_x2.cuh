@@ -34,6 +34,9 @@
 // rows and fragment layouts are checked against the oracle without a GPU.
 #pragma once
 #include "../../include/aether_b200.h"
+#ifndef AE_HOST_EMU
+#include "async_copy.cuh"
+#endif
 #include "fft_device.cuh"
 
 namespace ae {
@@ -357,6 +360,28 @@ AE_X2_DEV void x2_stage1(cx2 (&v)[16], const float2* __restrict__ src, const flo
   }
 }
 
+// first stage from registers: y[j] = sample at position t + 32 j (the layout x2_second_stage leaves its results in)
+template <bool INV>
+AE_X2_DEV void x2_stage1_regs(cx2 (&v)[16], const float2 (&y)[32], const X2Tw& tw) {
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const float2 a = y[m], b = y[m + 16];
+    const float2 e = make_float2(a.x + b.x, a.y + b.y), d = make_float2(a.x - b.x, a.y - b.y);
+    const float2 o = mul_tw<INV>(d, tw.s1[m]);
+    v[m] = cx2{make_float2(e.x, o.x), make_float2(e.y, o.y)};
+  }
+}
+// the lane's twiddle registers from the per-thread table (chain_x2_twiddles)
+template <int N>
+AE_X2_DEV void x2_load_twiddles(X2Tw& tw, const float2* __restrict__ table, int t) {
+  using XC = X2Cfg<N>;
+#pragma unroll
+  for (int m = 0; m < 16; ++m) tw.s1[m] = table[(XC::ROW_S1 + m) * XC::T + t];
+#pragma unroll
+  for (int i = 1; i < 4; ++i) { tw.wl[i] = table[(XC::ROW_P1 + i - 1) * XC::T + t]; tw.wh[i] = table[(XC::ROW_P1 + i + 2) * XC::T + t]; }
+  tw.wl[0] = tw.wh[0] = make_float2(1.0f, 0.0f);
+}
+
 // The two decision bytes of one bin as a little-endian u16: byte = sign of re / im, the im byte is 2
 // (compat=reference, idx & 2) or 1 (corrected); `mask` = 0x0201 / 0x0101
 AE_X2_DEV uint32_t x2_sign_pair(float2 v, uint32_t mask) {
@@ -449,6 +474,14 @@ AE_X2_DEV void chain_x2_body(const ChainX2Params& p, const X2Launch& L, unsigned
       src = xin;
     } else {
       src = p.x + frame * N;
+#ifndef AE_HOST_EMU
+      // plain loads have no look-ahead: pull this warp's next frame towards L2 (8 KB = 64 lines, two per lane)
+      if (frame + stride < p.frames) {
+        const char* pf = reinterpret_cast<const char*>(p.x + (frame + stride) * N) + 128 * t;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 4096));
+      }
+#endif
     }
     cx2 v[16];
     float2 y[32];

@@ -6,6 +6,7 @@
 // Parity tier T1: EVM against the f64 direct form (tests/test_gpu_fir.py).
 #include <cstdlib>
 
+#include "chain_x2.cuh"
 #include "fft_device.cuh"
 #include "internal.h"
 
@@ -260,6 +261,132 @@ fir_os_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_t n, co
       if (i >= ntaps - 1 && g < out_end) st_stream(y + g, v[m]);
     }
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K4b overlap-save for 1024-point blocks (up to 256 taps) on the transform of chain_x2.cuh: one WARP per segment,
+// 1024 = 32 x 32 with one shared-memory exchange per transform (K4 needs two, and a named barrier between the two
+// warps that share a segment), packed FP32 butterflies, persistent warps.  The forward transform leaves thread t with
+// bins t + 32 c, which is exactly the input layout of the inverse transform, so the spectrum is multiplied by H in
+// registers.  Same results as K4 up to rounding (both are checked against the f64 direct form).
+// -------------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+fir_os_x2_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_t n, const float2* __restrict__ H,
+                 const float2* __restrict__ twtab, int ntaps, int hist_len, const float2* __restrict__ history, size_t frame_len,
+                 size_t segs_per_frame, size_t n_segs) {
+  constexpr int NF = 1024;
+  using XC = X2Cfg<NF>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* Hs = reinterpret_cast<float2*>(smem_raw);                               // NF cf32
+  const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+  float2* ex = Hs + NF + (size_t)warp * (2 * XC::EX_ELEMS);                       // two planes of EX_ELEMS float2 per warp
+  for (int i = threadIdx.x; i < NF; i += 32 * WARPS) Hs[i] = __ldg(H + i);
+  X2Tw tw;
+  x2_load_twiddles<NF>(tw, twtab, t);
+  __syncthreads();
+  const long long L = NF - ntaps + 1;
+  for (size_t seg = (size_t)blockIdx.x * WARPS + warp; seg < n_segs; seg += (size_t)gridDim.x * WARPS) {
+    long long out_start, frame_start, out_end;
+    if (frame_len) {
+      const size_t fi = seg / segs_per_frame, si = seg % segs_per_frame;
+      frame_start = (long long)(fi * frame_len);
+      out_start = frame_start + (long long)si * L;
+      long long fe = frame_start + (long long)frame_len;
+      if (fe > (long long)n) fe = (long long)n;
+      out_end = out_start + L < fe ? out_start + L : fe;
+    } else {
+      frame_start = 0;
+      out_start = (long long)seg * L;
+      out_end = out_start + L < (long long)n ? out_start + L : (long long)n;
+    }
+    const long long in_start = out_start - (ntaps - 1);
+    const bool interior = in_start >= frame_start && out_end == out_start + L;
+    {
+      // pull this warp's NEXT segment towards L2 while the current one is transformed (plain loads have no
+      // look-ahead of their own; 8 KB = 64 lines = two per lane)
+      const size_t nseg = seg + (size_t)gridDim.x * WARPS;
+      if (!frame_len && nseg < n_segs) {
+        const long long ns = (long long)nseg * L - (ntaps - 1);
+        const char* pf = reinterpret_cast<const char*>(x + (ns > 0 ? ns : 0)) + 128 * t;
+        if ((long long)(ns + NF) <= (long long)n) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 4096));
+        }
+      }
+    }
+    float2 v32[32];
+    if (interior) {
+      const float2* src = x + in_start + t;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v32[j] = ld_stream(src + 32 * j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const long long g = in_start + t + 32 * j;
+        float2 s = make_float2(0.0f, 0.0f);
+        if (g >= frame_start) { if (g < out_end) s = ld_stream(x + g); }
+        else if (!frame_len && history && g >= -(long long)hist_len) s = __ldg(history + hist_len + g);
+        v32[j] = s;
+      }
+    }
+    cx2 v[16];
+    x2_stage1_regs<false>(v, v32, tw);
+    c2dft16<false>(v);
+    x2_second_stage<NF, false, false, false>(v, v32, ex, tw, t);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v32[c] = cx_mul(v32[c], Hs[t + 32 * c]);
+    x2_syncwarp();                                         // every lane is past its reads of the exchange buffer
+    x2_stage1_regs<true>(v, v32, tw);
+    c2dft16<true>(v);
+    x2_second_stage<NF, true, false, false>(v, v32, ex, tw, t);
+    if (interior) {
+      float2* dst = y + in_start + t;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (t + 32 * c >= ntaps - 1) st_stream(dst + 32 * c, v32[c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int i = t + 32 * c;
+        const long long g = out_start + i - (ntaps - 1);
+        if (i >= ntaps - 1 && g < out_end) st_stream(y + g, v32[c]);
+      }
+    }
+    x2_syncwarp();
+  }
+}
+
+template <int WARPS>
+static void launch_fir_os_x2_w(const float2* x, float2* y, size_t n, const float2* H, const float2* x2tw, size_t ntaps, const float2* history,
+                               size_t frame_len, cudaStream_t st) {
+  constexpr int NF = 1024;
+  using XC = X2Cfg<NF>;
+  const int hist_len = (int)(((ntaps + 7) / 8) * 8) - 1;
+  const size_t L = NF - ntaps + 1;
+  size_t segs_per_frame = 0, n_segs;
+  if (frame_len) {
+    segs_per_frame = (frame_len + L - 1) / L;
+    n_segs = ((n + frame_len - 1) / frame_len) * segs_per_frame;
+  } else {
+    n_segs = (n + L - 1) / L;
+  }
+  const size_t smem = (size_t)NF * sizeof(float2) + (size_t)WARPS * 2 * XC::EX_ELEMS * sizeof(float2);
+  const size_t resident = resident_ctas((const void*)fir_os_x2_kernel<WARPS>, 32 * WARPS, smem);
+  const size_t want = (n_segs + WARPS - 1) / WARPS;
+  fir_os_x2_kernel<WARPS><<<(unsigned)(want < resident ? want : resident), 32 * WARPS, smem, st>>>(
+      x, y, n, H, x2tw, (int)ntaps, hist_len, history, frame_len, segs_per_frame, n_segs);
+}
+
+void launch_fir_os_x2(const float2* x, float2* y, size_t n, const float2* H, const float2* x2tw, size_t ntaps, const float2* history,
+                      size_t frame_len, cudaStream_t st) {
+  if (n == 0) return;
+  static const char* we = getenv("AE_FIR_WARPS");
+  const int warps = we ? atoi(we) : 12;   // measured at 64 taps, 2^28 samples: 8 -> 311, 10 -> 297, 12 -> 342, 16 -> 304 Gsamples/s
+  if (warps >= 16) return launch_fir_os_x2_w<16>(x, y, n, H, x2tw, ntaps, history, frame_len, st);
+  if (warps >= 12) return launch_fir_os_x2_w<12>(x, y, n, H, x2tw, ntaps, history, frame_len, st);
+  if (warps >= 10) return launch_fir_os_x2_w<10>(x, y, n, H, x2tw, ntaps, history, frame_len, st);
+  return launch_fir_os_x2_w<8>(x, y, n, H, x2tw, ntaps, history, frame_len, st);
 }
 
 bool fir_os_supported(size_t nfft) { return nfft >= 256 && nfft <= 16384 && (nfft & (nfft - 1)) == 0; }

@@ -95,6 +95,9 @@ bool fir_os_supported(size_t nfft);
 // H = FFT_nfft(taps)/nfft (exp(-) convention); L = nfft - ntaps + 1 outputs per segment
 void launch_fir_overlap_save(const float2* x, float2* y, size_t n, const float2* H, const float2* tw, size_t nfft,
                              size_t ntaps, const float2* history, size_t frame_len, cudaStream_t st);
+// K4b: 1024-point blocks on the packed one-exchange transform of chain_x2.cuh; x2tw = chain_x2_twiddles rows
+void launch_fir_os_x2(const float2* x, float2* y, size_t n, const float2* H, const float2* x2tw, size_t ntaps, const float2* history,
+                      size_t frame_len, cudaStream_t st);
 // ---- K14 / K12 chains ------------------------------------------------------------------------
 bool chain_fused_supported(size_t nfft, size_t ntaps);
 // window[n] = s * sum_k h[k] exp(-sgn 2 pi i nk/N); taps in device memory

@@ -45,3 +45,41 @@ def sm_count() -> int:
     n = C.c_int(0)
     call("ae_sm_count", C.byref(n))
     return n.value
+
+
+class Graph:
+    """CUDA graph over the context stream (`ae_graph_*`): record the launches of a launch-bound step once, replay
+    them with one driver call.  Outputs must be sized before recording; nothing inside the bracket may synchronise.
+
+        with Graph() as g:          # records, does not run
+            for _ in range(16):
+                chain.modem_fused(...)
+        g.launch()                  # replays the 16 launches
+    """
+
+    def __init__(self):
+        self._h = None
+
+    def __enter__(self) -> "Graph":
+        call("ae_graph_begin")
+        return self
+
+    def __exit__(self, exc_type, exc, tb) -> bool:
+        h = C.c_void_p()
+        call("ae_graph_end", C.byref(h))
+        self._h = h
+        return False
+
+    def launch(self) -> None:
+        call("ae_graph_launch", self._h)
+
+    def close(self) -> None:
+        if self._h:
+            call("ae_graph_destroy", self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

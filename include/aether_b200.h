@@ -268,6 +268,19 @@ ae_status ae_pipe_send(ae_pipe* p, const ae_cf32* host_in, uint8_t* host_bits);
 ae_status ae_pipe_recv(ae_pipe* p, uint8_t** host_bits_done);
 size_t    ae_pipe_in_flight(const ae_pipe* p);      /* sent and not yet received */
 ae_status ae_pipe_report(ae_pipe* p, ae_pipe_stage stages[3], int reset);
+
+/* ---- CUDA graphs: launch-bound shapes (examples/modem.rs runs 1M symbols, a ~4 us kernel) ----------
+ * Between ae_graph_begin and ae_graph_end every launch the library makes on the context stream is RECORDED instead of
+ * run (cudaStreamBeginCapture); ae_graph_launch replays the whole recording with one driver call.  Rules of stream
+ * capture apply: size every output beforehand (nothing may reallocate) and call nothing that synchronises
+ * (downloads, ae_sync, ae_stats_read) inside the bracket.  Host-side state advances at record time: an Awgn stream
+ * offset is baked into each recorded launch, so the k launches of one recording use k consecutive noise blocks and
+ * every replay repeats them. */
+typedef struct ae_graph ae_graph;
+ae_status ae_graph_begin(void);
+ae_status ae_graph_end(ae_graph** out);
+ae_status ae_graph_launch(ae_graph* g);
+ae_status ae_graph_destroy(ae_graph* g);
 /* unfused composition of the same chain from the stand-alone kernels (for cross-checking) */
 ae_status ae_chain_exec_unfused(ae_chain* c, ae_vec* in, ae_bits* bits_out, ae_vec* symbols_out);
 

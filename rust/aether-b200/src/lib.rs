@@ -52,6 +52,14 @@ pub mod runtime {
     pub fn launch_count() -> u64 { unsafe { sys::ae_launch_count() } }
     /// Philox4x32-10 block (the AWGN generator's counter-based RNG), host side: known-answer checks
     pub fn philox4x32_10(ctr: [u32; 4], key: [u32; 2]) -> [u32; 4] { let mut o = [0u32; 4]; unsafe { ck(sys::ae_philox4x32_10(ctr.as_ptr(), key.as_ptr(), o.as_mut_ptr())) }; o }
+    /// CUDA graph over the context stream: `Graph::record(|| { ...library calls... })` records the launches instead of
+    /// running them, `launch()` replays them with one driver call (launch-bound shapes: the 1M-symbol modem loop-back)
+    pub struct Graph { h: *mut sys::ae_graph }
+    impl Graph {
+        pub fn record(f: impl FnOnce()) -> Self { unsafe { ck(sys::ae_graph_begin()) }; f(); let mut h = null_mut(); unsafe { ck(sys::ae_graph_end(&mut h)) }; Graph { h } }
+        pub fn launch(&mut self) { unsafe { ck(sys::ae_graph_launch(self.h)) } }
+    }
+    impl Drop for Graph { fn drop(&mut self) { unsafe { sys::ae_graph_destroy(self.h); } } }
     /// page-locked host buffer for the host pipelines (`Pipe`, `FftFirDemod::run_host`)
     pub struct PinnedBuf { pub ptr: *mut c_void, pub bytes: usize }
     impl PinnedBuf { pub fn new(bytes: usize) -> Self { let mut p = null_mut(); unsafe { ck(sys::ae_host_alloc(bytes, &mut p)) }; PinnedBuf { ptr: p, bytes } } }
