@@ -39,6 +39,7 @@ struct Ctx {
   std::vector<ae_vec*> pending;               // vecs with a non-empty tape
   std::map<size_t, float2*> tw_cache;         // plain twiddle tables W[k] by length (any-length path)
   std::map<size_t, float2*> ttw_cache;        // per-thread twiddle tables of the power-of-two kernels
+  float2* x2tw1024 = nullptr;                 // per-thread twiddle rows of the packed 32x32 transform (chain_x2.cuh)
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
 };
 
@@ -169,6 +170,22 @@ ae_status get_thread_twiddles(Ctx* c, size_t n, float2** out) {
   CK(cudaStreamSynchronize(c->stream));
   c->ttw_cache[n] = (float2*)p;
   *out = (float2*)p;
+  return AE_OK;
+}
+
+// twiddle rows of the packed one-exchange 1024-point transform (K14b / K4b / correlator), one table per device
+ae_status get_x2_twiddles(Ctx* c, float2** out) {
+  if (!c->x2tw1024) {
+    std::vector<float2> tw, hi, lo;
+    const float2 one = make_float2(1.f, 0.f);
+    chain_x2_tables(1024, &one, 1, tw, hi, lo);
+    void* p = nullptr;
+    TRY(dev_alloc(c, tw.size() * sizeof(float2), &p));
+    CK(cudaMemcpyAsync(p, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->x2tw1024 = (float2*)p;
+  }
+  *out = c->x2tw1024;
   return AE_OK;
 }
 
@@ -2039,6 +2056,14 @@ ae_status ae_correlate(ae_fft* f, ae_vec* inout, ae_vec* sig, int scale_kind, fl
   TRY(before_read(sig));
   const size_t n = f->len;
   const float s = scale_factor(scale_kind, n, x);
+  static const char* corr_v1 = getenv("AE_CORR_V1");   // developer switch: the two-exchange kernel for 1024 points too
+  if (n == 1024 && !corr_v1) {
+    float2* x2tw;
+    TRY(get_x2_twiddles(c, &x2tw));
+    launch_correlate_x2(vptr(inout), vptr(sig), howmany, x2tw, f->compat == AE_COMPAT_REFERENCE, s, scale_kind != AE_SCALE_NONE, c->stream);
+    CKL(1);
+    return AE_OK;
+  }
   if (f->pow2 && spectral_supported(n)) {
     launch_correlate(vptr(inout), vptr(sig), n, howmany, f->tw, f->compat == AE_COMPAT_REFERENCE, s, scale_kind != AE_SCALE_NONE,
                      c->stream);

@@ -56,7 +56,7 @@ static void launch_x2_dir(const ChainX2Params& p, cudaStream_t st) {
   static const char* warps_env = getenv("AE_CHAIN_WARPS");
   const bool staged = ((uintptr_t)p.x % 16) == 0 && !no_tma;
   // 8 warps (2 per sub-partition) measured best: the kernel is bound by instruction dispatch, not by latency
-  const int warps = warps_env ? atoi(warps_env) : (staged ? 8 : 12);
+  const int warps = warps_env ? atoi(warps_env) : (staged ? 8 : 16);   // multiples of 4 only: 10 or 14 warps leave the sub-partitions unbalanced (measured 12 % slower)
   if (staged) {
     if (warps <= 4) launch_x2<INV, true, 4>(p, st);
     else if (warps <= 8) launch_x2<INV, true, 8>(p, st);

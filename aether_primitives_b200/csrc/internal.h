@@ -121,6 +121,9 @@ bool spectral_supported(size_t n);
 void launch_spectrogram(const float2* in, size_t n_samples, float* levels, size_t n, size_t frames, const float2* tw, bool inverse,
                         float scale, int use_db, cudaStream_t st);
 void launch_levels(const float2* spec, float* levels, size_t total, size_t n, int use_db, cudaStream_t st);
+// 1024-point frames on the packed one-exchange transform (warp per frame); x2tw = chain_x2_twiddles rows
+void launch_correlate_x2(float2* data, const float2* sig, size_t frames, const float2* x2tw, bool fwd_inverse, float scale, int do_scale,
+                         cudaStream_t st);
 void launch_correlate(float2* data, const float2* sig, size_t n, size_t frames, const float2* tw, bool fwd_inverse, float scale,
                       int do_scale, cudaStream_t st);
 

@@ -5,6 +5,7 @@
 //   correlate   : the frequency-domain correlator the crate benchmarks (benches/benches.rs:410-416):
 //                 vec_rfft(s) -> vec_mul(sig) -> vec_rifft(s) per frame in ONE kernel; the spectrum
 //                 never leaves registers (forward output layout == inverse input layout).
+#include "chain_x2.cuh"
 #include "fft_device.cuh"
 #include "internal.h"
 
@@ -140,6 +141,70 @@ correlate_kernel(float2* __restrict__ data, const float2* __restrict__ sig, cons
     }
     if (C::NP > 1) frame_sync<C::T>(f);
   }
+}
+
+// Same chain for 1024-point frames on the packed one-exchange transform of chain_x2.cuh: a warp per frame, the forward
+// result (thread t: bins t + 32 c) is the inverse transform's input layout, so scale, multiply and the second transform
+// stay in registers; one shared-memory exchange per transform instead of two, no barrier between warps.
+template <bool FWD_INV, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1)
+correlate_x2_kernel(float2* __restrict__ data, const float2* __restrict__ sig, const float2* __restrict__ twtab, size_t frames, float scale,
+                    int do_scale) {
+  constexpr int N = 1024;
+  using XC = X2Cfg<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* sg = reinterpret_cast<float2*>(smem_raw);                               // N cf32: the reference signal's spectrum operand
+  const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+  float2* ex = sg + N + (size_t)warp * (2 * XC::EX_ELEMS);
+  for (int i = threadIdx.x; i < N; i += 32 * WARPS) sg[i] = __ldg(sig + i);
+  X2Tw tw;
+  x2_load_twiddles<N>(tw, twtab, t);
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * WARPS;
+  for (size_t frame = (size_t)blockIdx.x * WARPS + warp; frame < frames; frame += stride) {
+    float2* p = data + frame * N + t;
+    if (frame + stride < frames) {   // next frame of this warp towards L2 (plain loads have no look-ahead)
+      const char* pf = reinterpret_cast<const char*>(data + (frame + stride) * N) + 128 * t;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 4096));
+    }
+    float2 y[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = ld_stream(p + 32 * j);
+    cx2 v[16];
+    x2_stage1_regs<FWD_INV>(v, y, tw);
+    c2dft16<FWD_INV>(v);
+    x2_second_stage<N, FWD_INV, false, false>(v, y, ex, tw, t);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (do_scale) y[c] = cx_scale_exact(y[c], scale);                 // Scale of vec_rfft
+      y[c] = cx_mul_exact(y[c], sg[t + 32 * c]);                        // vec_mul: unfused arithmetic
+    }
+    x2_syncwarp();
+    x2_stage1_regs<!FWD_INV>(v, y, tw);
+    c2dft16<!FWD_INV>(v);
+    x2_second_stage<N, !FWD_INV, false, false>(v, y, ex, tw, t);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (do_scale) y[c] = cx_scale_exact(y[c], scale);                 // Scale of vec_rifft
+      st_stream(p + 32 * c, y[c]);
+    }
+    x2_syncwarp();
+  }
+}
+void launch_correlate_x2(float2* data, const float2* sig, size_t frames, const float2* x2tw, bool fwd_inverse, float scale, int do_scale,
+                         cudaStream_t st) {
+  if (frames == 0) return;
+  constexpr int WARPS = 12;
+  using XC = X2Cfg<1024>;
+  const size_t smem = (size_t)1024 * sizeof(float2) + (size_t)WARPS * 2 * XC::EX_ELEMS * sizeof(float2);
+  const size_t want = (frames + WARPS - 1) / WARPS;
+  auto launch = [&](auto kern) {
+    const size_t resident = resident_ctas((const void*)kern, 32 * WARPS, smem);
+    kern<<<(unsigned)(want < resident ? want : resident), 32 * WARPS, smem, st>>>(data, sig, x2tw, frames, scale, do_scale);
+  };
+  if (fwd_inverse) launch(correlate_x2_kernel<true, WARPS>);
+  else launch(correlate_x2_kernel<false, WARPS>);
 }
 
 template <int N>
