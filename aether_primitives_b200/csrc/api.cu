@@ -81,6 +81,7 @@ namespace {
 thread_local const char* t_unsupported = nullptr;
 struct ResKey { const void* k; int dev; int threads; size_t smem; bool operator<(const ResKey& o) const { return std::tie(k, dev, threads, smem) < std::tie(o.k, o.dev, o.threads, o.smem); } };
 std::map<ResKey, size_t> g_resident;
+std::map<std::pair<const void*, int>, size_t> g_optin;   // largest dynamic shared-memory opt-in made per (kernel, device)
 std::mutex g_resident_mu;
 }  // namespace
 void note_unsupported_launch(const char* what) { t_unsupported = what; }
@@ -92,7 +93,13 @@ size_t resident_ctas(const void* kern, int threads, size_t smem) {
   std::lock_guard<std::mutex> lk(g_resident_mu);
   auto it = g_resident.find(key);
   if (it != g_resident.end()) return it->second;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the opt-in is one value per kernel: only ever raise it (a kernel is launched with several sizes, e.g. the
+  // any-length FFT; lowering it would make an earlier, larger configuration fail with "invalid argument")
+  size_t& optin = g_optin[std::make_pair(kern, dev)];
+  if (smem > 48 * 1024 && smem > optin) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    optin = smem;
+  }
   int per_sm = 1, sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;

@@ -285,14 +285,20 @@ def extras(torch, ae, d_in, frames, hbm_peak, steps=5, warmup=3, rank=0, world=1
         if nsym == 1_000_000:
             # the as-specified size is launch-bound (a ~4 us kernel): 16 steps recorded into one CUDA graph (ae_graph_*)
             reps = 16
-            ae.chain.modem_fused(qpsk, g, bits_in, bits_out, st, ae.COMPAT_REFERENCE)
-            with ae.Graph() as gr:
-                for _ in range(reps):
-                    ae.chain.modem_fused(qpsk, g, bits_in, bits_out, st, ae.COMPAT_REFERENCE)
-            t = timed(torch, gr.launch, steps, warmup) / steps / reps
+            cap = torch.cuda.Stream()          # capture needs a real stream: the legacy default stream cannot be captured
+            torch.cuda.synchronize()
+            with torch.cuda.stream(cap):
+                ae.use_torch_stream()
+                ae.chain.modem_fused(qpsk, g, bits_in, bits_out, st, ae.COMPAT_REFERENCE)
+                with ae.Graph() as gr:
+                    for _ in range(reps):
+                        ae.chain.modem_fused(qpsk, g, bits_in, bits_out, st, ae.COMPAT_REFERENCE)
+                t = timed(torch, gr.launch, steps, warmup) / steps / reps
+                gr.close()
+            torch.cuda.synchronize()
+            ae.use_torch_stream()
             rec("modem_fused_%dsym_graph16" % nsym, 4.0 * nsym, t, nsym, "symbols")
             out["modem_fused_%dsym_graph16" % nsym]["us_per_step"] = t * 1e6
-            gr.close()
         del bits_in, bits_out
     # config 1 stand-alone pieces: modulate, Awgn::apply, Awgn::fill, demod on 2^26 symbols
     nsym = 1 << 26
