@@ -134,7 +134,7 @@ def test_committed_bench_line_carries_the_contract_keys():
     import json
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    lines = sorted(glob.glob(os.path.join(root, "profiles", "r1_bench_v[0-9]*.json")), key=lambda p: int(re.findall(r"_v(\d+)", p)[0]))
+    lines = sorted(glob.glob(os.path.join(root, "profiles", "r[0-9]_bench_v[0-9]*.json")), key=lambda p: (int(re.findall(r"r(\d+)_bench", p)[0]), int(re.findall(r"_v(\d+)", p)[0])))
     d = json.load(open(lines[-1]))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
