@@ -1699,6 +1699,9 @@ ae_status ae_chain_exec(ae_chain* ch, ae_vec* in, ae_bits* bits_out) {
   if (!ch || !in || !bits_out) return fail(AE_EARG, "null");
   if (in->len % ch->n) return fail(AE_ELEN, "Input and FFT must be the same length");
   if (!ch->fused) return ae_chain_exec_unfused(ch, in, bits_out, nullptr);
+  // the fused kernels write the two bytes of a symbol with one 16-bit (K14) or 32-bit (K14b) store: a wrapped bit
+  // buffer at an odd address takes the composition of the stand-alone kernels
+  if ((reinterpret_cast<uintptr_t>(bits_out->a->p) + bits_out->off) & 1) return ae_chain_exec_unfused(ch, in, bits_out, nullptr);
   Ctx* c = ch->c;
   cudaSetDevice(c->dev);
   const size_t frames = in->len / ch->n;

@@ -434,6 +434,22 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {   // selector nibble bit 3: replicate the byte's sign
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ float fmax3_nan(float a, float b, float c) {   // FMNMX3, NaN-propagating
+  float d;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // =================================================================================================
 // K10 modem_fused (examples/modem.rs:15-32): modulate -> Awgn::apply -> demod_naive (+ bit errors)
 // in registers.  4 B/symbol of HBM traffic for QPSK: 2 B bits in + 2 B bits out.
@@ -497,7 +513,49 @@ __global__ void __launch_bounds__(256) modem_kernel(const __grid_constant__ ModT
         }
       }
     };
-    if (full) {
+    // Fast path for the crate's own QPSK table (+-1, +-1) with every bit byte 0 or 1: the constellation point is
+    // sigma = 1 - 2 bit per component and fl(sigma + n) = sigma * fl(1 + sigma n) exactly (IEEE rounding is symmetric),
+    // so one FADD on the sign-flipped noise gives |component| and, as its sign, "this bit was received wrong".
+    // The reference's nearest-point search agrees with the sign test unless a component is within the bound of
+    // demod_qpsk_generic() of an axis, NaN or inf: one test per thread on the minimum and NaN-propagating maximum of
+    // its eight components, the general code below otherwise.
+    bool fast_done = false;
+    if (M == 4 && full && generic) {
+      const uint2 w = *reinterpret_cast<const uint2*>(bi);
+      if (((w.x | w.y) & 0xfefefefeu) == 0u) {
+        const uint32_t sx = w.x << 7, sy = w.y << 7;       // bit 7 of every byte = the bit
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 nz = cx_scale_exact(z[i], scale);
+          if (twice) nz = cx_scale_exact(nz, scale);
+          const uint32_t src = i < 2 ? sx : sy;
+          const uint32_t mre = prmt_b32(src, 0u, 0x8888u + 0x1111u * (2 * (i & 1)));       // all ones when the bit is set
+          const uint32_t mim = prmt_b32(src, 0u, 0x8888u + 0x1111u * (2 * (i & 1) + 1));
+          r[2 * i] = __fadd_rn(1.0f, __uint_as_float(__float_as_uint(nz.x) ^ (mre & 0x80000000u)));
+          r[2 * i + 1] = __fadd_rn(1.0f, __uint_as_float(__float_as_uint(nz.y) ^ (mim & 0x80000000u)));
+        }
+        float mx = fmax3_nan(fabsf(r[0]), fabsf(r[1]), fabsf(r[2])), mn = fmin3(fabsf(r[0]), fabsf(r[1]), fabsf(r[2]));
+        mx = fmax3_nan(mx, fabsf(r[3]), fabsf(r[4])); mn = fmin3(mn, fabsf(r[3]), fabsf(r[4]));
+        mx = fmax3_nan(mx, fabsf(r[5]), fabsf(r[6])); mn = fmin3(mn, fabsf(r[5]), fabsf(r[6]));
+        mx = fmax3_nan(mx, fabsf(r[7]), fabsf(r[7])); mn = fmin3(mn, fabsf(r[7]), fabsf(r[7]));
+        const float uu = fmaf(mx, 6.9053396600248786e-4f, 6.9053396600248786e-4f);          // 2^-10.5 (1 + max)
+        if (mn > uu * uu) {
+          // bytes of e: 0xff where the received bit differs from the sent one
+          const uint32_t e0 = prmt_b32(prmt_b32(__float_as_uint(r[0]), __float_as_uint(r[1]), 0x00FBu),
+                                       prmt_b32(__float_as_uint(r[2]), __float_as_uint(r[3]), 0x00FBu), 0x5410u);
+          const uint32_t e1 = prmt_b32(prmt_b32(__float_as_uint(r[4]), __float_as_uint(r[5]), 0x00FBu),
+                                       prmt_b32(__float_as_uint(r[6]), __float_as_uint(r[7]), 0x00FBu), 0x5410u);
+          uint32_t o0 = w.x ^ (e0 & 0x01010101u), o1 = w.y ^ (e1 & 0x01010101u);
+          if (compat == AE_COMPAT_REFERENCE) { o0 += o0 & 0x01000100u; o1 += o1 & 0x01000100u; }   // second byte = idx & 2
+          *reinterpret_cast<uint2*>(bo) = make_uint2(o0, o1);
+          errs += (unsigned)(__popc(e0) + __popc(e1)) >> 3;
+          fast_done = true;
+        }
+      }
+    }
+    if (fast_done) {
+    } else if (full) {
       body(std::false_type{});
       // a bit is in error when exactly one of (sent, received) is non-zero: compare the non-zero masks
       if (BPS == 2) {

@@ -391,15 +391,51 @@ __device__ __forceinline__ void odd_dft(float2 (&v)[P], const float2 (&root)[(P 
   for (int i = 0; i < P; ++i) v[i] = o[i];
 }
 
+// Composite radix P = P1 * P2 with P1 in {2, 4}, P2 an odd prime, coprime: Good-Thomas prime-factor mapping, no
+// twiddles inside the butterfly.   n = (P2 n1 + P1 n2) mod P,  k = (P2 c1 k1 + P1 c2 k2) mod P  with
+// c1 = P2^-1 mod P1, c2 = P1^-1 mod P2:   X[k] = sum_n1 W_P1^(n1 k1) sum_n2 W_P2^(n2 k2) x[n].
+// One pass of radix 10 replaces a radix-5 and a radix-2 pass (N = 1000: three passes instead of four; the passes are
+// bound by the shared-memory pipe).  A constant input still gives exact zeros off DC (odd_dft is DC-exact, the
+// power-of-two butterflies are sums and differences).
+constexpr int pfa_inv_mod(int a, int m) {
+  for (int x = 1; x < m; ++x)
+    if ((a * x) % m == 1) return x;
+  return 1;
+}
+template <int P1, int P2>
+__device__ __forceinline__ void pfa_dft(float2 (&v)[P1 * P2], const float2 (&root)[(P2 - 1) / 2 + 1]) {
+  constexpr int P = P1 * P2;
+  float2 s[P1][P2];
+#pragma unroll
+  for (int n1 = 0; n1 < P1; ++n1) {
+#pragma unroll
+    for (int n2 = 0; n2 < P2; ++n2) s[n1][n2] = v[(P2 * n1 + P1 * n2) % P];
+    odd_dft<P2>(s[n1], root);
+  }
+  constexpr int c1 = pfa_inv_mod(P2 % P1, P1), c2 = pfa_inv_mod(P1 % P2, P2);
+#pragma unroll
+  for (int k2 = 0; k2 < P2; ++k2) {
+    float2 c[P1];
+#pragma unroll
+    for (int n1 = 0; n1 < P1; ++n1) c[n1] = s[n1][k2];
+    Dft<P1, false>::run(c);
+#pragma unroll
+    for (int k1 = 0; k1 < P1; ++k1) v[(P2 * c1 * k1 + P1 * c2 * k2) % P] = c[k1];
+  }
+}
+// the odd prime inside a radix handled by gen_butterfly_pass (0: a power of two)
+__host__ __device__ constexpr int gen_odd_part(int p) { return (p & 1) ? p : (p == 6 || p == 12) ? 3 : (p == 10) ? 5 : 0; }
+
 template <int P, bool SRC_SMEM, bool DST_SMEM>
 __device__ __forceinline__ void gen_butterfly_pass(const float2* src, float2* dst, const float2* __restrict__ tw, unsigned n, const GenPass& gp,
                                                    unsigned slots, bool conj_in, bool conj_out, bool do_scale, float scale) {
   const unsigned m = gp.m, tws = gp.tws, ns = gp.ns;
-  constexpr int H = (P - 1) / 2;
+  constexpr int PO = gen_odd_part(P);                    // roots of unity of the odd factor: exp(-2 pi i r / PO) = tw[r n / PO]
+  constexpr int H = PO ? (PO - 1) / 2 : 0;
   float2 root[H + 1];
-  if constexpr (P & 1) {
+  if constexpr (PO != 0) {
 #pragma unroll
-    for (int r = 1; r <= H; ++r) root[r] = __ldg(tw + r * m);
+    for (int r = 1; r <= H; ++r) root[r] = __ldg(tw + r * (m * (P / PO)));
   }
   for (unsigned item = threadIdx.x; item < slots * m; item += blockDim.x) {
         const unsigned s = gen_div(item, gp.mg_m), j = item - s * m, k = j - gen_div(j, gp.mg_ns) * ns, sb = s * n;
@@ -415,12 +451,23 @@ __device__ __forceinline__ void gen_butterfly_pass(const float2* src, float2* ds
       // by the L1/shared-memory pipe, not by FP32 issue; each product costs about one ulp)
       float2 w[P];
       w[1] = __ldg(tw + k * tws);
+      if constexpr (P >= 10) {
+        // the composite radices reach W^9 .. W^11: three table reads (r k tws < n, no wrap) keep every power within two
+        // products of a table entry, so the pass is as accurate as the prime-radix passes it replaces
+        w[2] = __ldg(tw + 2 * k * tws);
+        w[4] = __ldg(tw + 4 * k * tws);
+        w[3] = cx_mul(w[1], w[2]);
 #pragma unroll
-      for (int r = 2; r < P; ++r) w[r] = cx_mul(w[r / 2], w[r - r / 2]);
+        for (int r = 5; r < P; ++r) w[r] = cx_mul(w[r - 4], w[4]);
+      } else {
+#pragma unroll
+        for (int r = 2; r < P; ++r) w[r] = cx_mul(w[r / 2], w[r - r / 2]);
+      }
 #pragma unroll
       for (int r = 1; r < P; ++r) v[r] = cx_mul(v[r], w[r]);
     }
     if constexpr (P & 1) odd_dft<P>(v, root);
+    else if constexpr (PO != 0) pfa_dft<P / PO, PO>(v, root);
     else Dft<P, false>::run(v);
     const unsigned d0 = sb + (j - k) * P + k;
 #pragma unroll
@@ -472,14 +519,14 @@ __device__ __forceinline__ void gen_output_pass(const float2* src, float2* dst, 
 }
 
 __host__ __device__ constexpr bool gen_has_butterfly(unsigned p) {
-  return p == 2 || p == 3 || p == 4 || p == 5 || p == 7 || p == 8 || p == 11 || p == 13;
+  return p == 2 || p == 3 || p == 4 || p == 5 || p == 6 || p == 7 || p == 8 || p == 10 || p == 11 || p == 12 || p == 13;
 }
 template <bool SRC_SMEM, bool DST_SMEM>
 __device__ __forceinline__ void gen_pass(const GenPass& gp, unsigned mg_n, const float2* src, float2* dst, const float2* __restrict__ tw,
                                          unsigned n, unsigned slots, bool conj_in, bool conj_out, bool do_scale, float scale) {
   switch (gp.p) {
 #define AE_P(PP) case PP: gen_butterfly_pass<PP, SRC_SMEM, DST_SMEM>(src, dst, tw, n, gp, slots, conj_in, conj_out, do_scale, scale); break;
-    AE_P(2) AE_P(3) AE_P(4) AE_P(5) AE_P(7) AE_P(8) AE_P(11) AE_P(13)
+    AE_P(2) AE_P(3) AE_P(4) AE_P(5) AE_P(6) AE_P(7) AE_P(8) AE_P(10) AE_P(11) AE_P(12) AE_P(13)
 #undef AE_P
     default: gen_output_pass<SRC_SMEM, DST_SMEM>(src, dst, tw, n, gp, mg_n, slots, conj_in, conj_out, do_scale, scale); break;
   }
@@ -541,16 +588,29 @@ void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n
                         const uint32_t* radices, int n_radices, bool inverse, bool do_scale, float scale, cudaStream_t st) {
   if (frames == 0 || n == 0) return;
   if (n <= (size_t)kGenSmemMaxN && n_radices >= 1 && n_radices <= kGenMaxRadices) {
-    // odd radices first (their stride-P stores are conflict-free), then the powers of two merged into 8s
+    // odd radices first (their stride-P stores are conflict-free), then 5 x 2 -> 10, 3 x 4 -> 12, 3 x 2 -> 6 (fewer
+    // passes: each one moves the whole frame through shared memory), then the powers of two merged into 8s
+    static const bool composite = getenv("AE_FFT_NO_COMPOSITE") == nullptr;
     unsigned order[kGenMaxRadices];
     int cnt = 0;
-    unsigned twos = 0;
+    unsigned twos = 0, threes = 0, fives = 0;
     for (int i = 0; i < n_radices; ++i) {
       if (radices[i] == 2) twos += 1;
       else if (radices[i] == 4) twos += 2;
       else if (radices[i] == 8) twos += 3;
+      else if (radices[i] == 3 && composite) threes += 1;
+      else if (radices[i] == 5 && composite) fives += 1;
       else order[cnt++] = radices[i];
     }
+    unsigned tens = 0, twelves = 0, sixes = 0;
+    while (fives && twos) { ++tens; --fives; --twos; }
+    while (threes && twos >= 2) { ++twelves; --threes; twos -= 2; }
+    while (threes && twos) { ++sixes; --threes; --twos; }
+    for (; threes; --threes) order[cnt++] = 3;
+    for (; fives; --fives) order[cnt++] = 5;
+    for (; tens; --tens) order[cnt++] = 10;
+    for (; twelves; --twelves) order[cnt++] = 12;
+    for (; sixes; --sixes) order[cnt++] = 6;
     for (; twos >= 3 && cnt < kGenMaxRadices; twos -= 3) order[cnt++] = 8;
     if (twos == 2) order[cnt++] = 4;
     if (twos == 1) order[cnt++] = 2;

@@ -246,6 +246,10 @@ def extras(torch, ae, d_in, frames, hbm_peak, steps=5, warmup=3, rank=0, world=1
     ds = ae.DeviceVec.zeros(m // 4)
     t = timed(torch, lambda: ae.sampling.downsample(a, ds), steps, warmup) / steps
     rec("downsample_by4", 16.0 * (m // 4), t, m // 4, "outputs")
+    # the kept samples are 32 bytes apart = one DRAM sector each, so every sector of the input is fetched
+    # (ncu: dram__bytes_read = the whole input, profiles/r2_all_kernels_ncu_summary.txt): the floor is 40 B/output
+    out["downsample_by4"]["dram_sector_GB/s"] = 40.0 * (m // 4) / t / 1e9
+    out["downsample_by4"]["frac_hbm_dram_sector"] = out["downsample_by4"]["dram_sector_GB/s"] / hbm_peak
     src = d_in.view(0, m // 4)
     dst = ae.DeviceVec.with_capacity(m)
 

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "aether_b200.hpp"
 
@@ -135,6 +136,75 @@ int main() {
       if (v > vmax) { vmax = v; imax = i; }
     }
     if (st.n != x.size() || st.max_idx != imax || st.max_val != vmax) { std::printf("FAIL vec_stats\n"); return 1; }
+  }
+  {  // multi-GPU and fused surface: counters, communicator (one rank), graph replay, sharded FIR, modem / OFDM kernels
+    Modulation m = qpsk();
+    Awgn g = noise::generator();
+    g.set_power(0.5f);
+    DeviceBits tx = sequence::generate(sequence::expand(1, 31).to_host(), {28, 31}, 4096), rx(4096);   // src/sequence.rs:41-46
+    DeviceStats st;
+    chain::modem_fused(m, g, tx, rx, &st, Compat::Corrected);
+    if (g.tell() != 2048) { std::printf("FAIL awgn tell after modem_fused\n"); return 1; }
+    ae_stats a = st.read();
+    DeviceStats st2;
+    st2.count_bit_errors(tx, rx);
+    if (a.n_bits != 4096 || a.bit_errors == 0 || a.bit_errors != st2.read().bit_errors) { std::printf("FAIL modem_fused counters\n"); return 1; }
+    // the same noise stream again: seek back, apply on the stand-alone kernels
+    g.seek(0);
+    DeviceVec sym = m.modulate(tx);
+    g.apply(sym);
+    DeviceBits rx2(4096);
+    m.demod_naive(sym, rx2, Compat::Corrected);
+    if (rx2.to_host() != rx.to_host()) { std::printf("FAIL modem_fused vs stand-alone kernels\n"); return 1; }
+    // OFDM counters: two half-runs with global frame ids == one run; all-reduce over a one-rank communicator is the identity
+    DeviceStats whole, halves;
+    chain::ofdm_chain(2048, 8, 0, 0.5f, 7, &whole);
+    chain::ofdm_chain(2048, 4, 0, 0.5f, 7, &halves);
+    chain::ofdm_chain(2048, 4, 4, 0.5f, 7, &halves);
+    const ae_stats w = whole.read(), h = halves.read();
+    if (w.bit_errors != h.bit_errors || w.n_bits != h.n_bits || w.n_bits != 2u * 2048u * 8u) { std::printf("FAIL ofdm_chain counters\n"); return 1; }
+    Comm c = Comm::init_rank(Comm::unique_id(), 1, 0);
+    if (c.info().nranks != 1 || c.info().rank != 0) { std::printf("FAIL comm info\n"); return 1; }
+    c.allreduce(whole);
+    if (whole.read().bit_errors != w.bit_errors) { std::printf("FAIL one-rank allreduce\n"); return 1; }
+    // CUDA graph: three recorded vec_scale launches, replayed twice
+    DeviceVec v(rep({1, 1}, 256));
+    Graph gr = Graph::record([&] { for (int i = 0; i < 3; ++i) v.vec_scale(2.0f).flush(); });
+    gr.launch();
+    gr.launch();
+    assert_evm(v.to_host(), rep({64, 64}, 256), -80, "graph replay");
+    // sharded FIR: three shards of one stream == the unsharded filter, bit for bit
+    std::vector<cf32> taps(64), x(40000);
+    for (size_t k = 0; k < taps.size(); ++k) taps[k] = cf32(1.f / (1.f + k), 0.01f * k);
+    uint32_t lcg = 99;
+    for (auto& e : x) { lcg = lcg * 1664525u + 1013904223u; e = cf32((float)(lcg >> 8) / 8388608.f - 1.f, (float)(lcg & 0xffff) / 32768.f - 1.f); }
+    Fir whole_f(taps, 0, AE_FIR_OVERLAP_SAVE);
+    DeviceVec dx(x), dy(x.size());
+    whole_f.filter(dx, dy);
+    const std::vector<cf32> want = dy.to_host();
+    for (int r = 0; r < 3; ++r) {
+      ShardedFir sf(taps, x.size(), r, 3, AE_FIR_OVERLAP_SAVE);
+      DeviceVec in(std::vector<cf32>(x.begin() + sf.lo_in, x.begin() + sf.hi_in)), work(sf.hi_in - sf.lo_in);
+      const std::vector<cf32> got = sf.filter(in, work).to_host();
+      if (got.size() != sf.hi - sf.lo || std::memcmp(got.data(), want.data() + sf.lo, got.size() * sizeof(cf32)) != 0) {
+        std::printf("FAIL sharded FIR, shard %d\n", r);
+        return 1;
+      }
+    }
+    // spectrogram of a DC frame: all power in the middle bin; correlator of a frame with itself peaks at lag 0
+    Cfft f = Cfft::with_len(1024);
+    DeviceVec dc(rep({1, 0}, 1024));
+    DeviceF32 lev(1024);
+    f.spectrogram(dc, lev, false);
+    const std::vector<float> l = lev.to_host();
+    size_t arg = 0;
+    for (size_t i = 0; i < l.size(); ++i) if (l[i] > l[arg]) arg = i;
+    if (arg != 512) { std::printf("FAIL spectrogram DC bin at %zu\n", arg); return 1; }
+    DeviceVec p(std::vector<cf32>(x.begin(), x.begin() + 1024)), q(std::vector<cf32>(x.begin(), x.begin() + 1024));
+    f.correlate(p, q, Scale::N());
+    const std::vector<cf32> corr = p.to_host();
+    for (size_t i = 1; i < corr.size(); ++i) if (std::abs(corr[i]) >= std::abs(corr[0])) { std::printf("FAIL correlator peak\n"); return 1; }
+    if (version().empty() || device_count() < 1 || sm_count() < 1 || launch_count() == 0) { std::printf("FAIL runtime info\n"); return 1; }
   }
   sync();
   std::printf("host mirror ok\n");

@@ -87,3 +87,51 @@ def test_two_ranks_nccl_counters_and_fir_shards():
         assert abs(res["ofdm"]["reduced"][k] - res["ofdm"]["single"][k]) <= 1e-11 * abs(res["ofdm"]["single"][k])
     assert res["fir"]["bit_identical"] is True
     assert res["chain"]["bit_identical"] is True
+
+
+def test_single_process_communicator_on_one_gpu(ae):
+    """ae_comm_init_all(1) + ae_stats_allreduce / _all: the library binds libnccl at run time; with one rank the
+    reduction is the identity (the >= 2 rank case is test_two_ranks_nccl_counters_and_fir_shards)"""
+    import ctypes as C
+
+    from aether_primitives_b200._lib import call
+    from aether_primitives_b200.stats import Comm, DeviceStats
+
+    h = (C.c_void_p * 1)()
+    call("ae_comm_init_all", 1, h)
+    comm = Comm(C.c_void_p(h[0]))
+    assert comm.info() == {"nranks": 1, "rank": 0, "device": 0}
+    st = DeviceStats()
+    ae.chain.ofdm_chain(1024, 16, 0, 0.5, 5, st, None, None, ae.COMPAT_CORRECTED)
+    before = st.read()
+    st.allreduce(comm)
+    assert st.read() == before and before["n_bits"] == 2 * 1024 * 16
+    sp = (C.c_void_p * 1)(st._h.value if hasattr(st._h, "value") else st._h)
+    cp = (C.c_void_p * 1)(h[0])
+    call("ae_stats_allreduce_all", sp, cp, 1)
+    assert st.read() == before
+    # one-process-per-GPU form with a single rank
+    c2 = Comm.init_rank(Comm.unique_id(), 1, 0)
+    st.allreduce(c2)
+    assert st.read() == before
+    c2.close()
+    comm.close()
+
+
+def test_chain_with_odd_bit_buffer_address(ae):
+    """a wrapped bit buffer at an odd address cannot take 16/32-bit stores: the chain falls back to the stand-alone kernels"""
+    import torch
+
+    from aether_primitives_b200.chain import FftFirDemod
+
+    x, h = rnd(4 * 1024, 3), taps(64)
+    ch = FftFirDemod(1024, h)
+    want = ae.DeviceBits.with_capacity(1)
+    ch.run(ae.DeviceVec.from_numpy(x), want)
+    raw = torch.zeros(2 * x.size + 1, dtype=torch.uint8, device="cuda")
+    odd = ae.DeviceBits.wrap(raw.data_ptr() + 1, 2 * x.size, owner=raw)
+    ch.run(ae.DeviceVec.from_numpy(x), odd)
+    got = raw[1:].cpu().numpy()
+    w = want.to_numpy()
+    mism = np.nonzero((got != 0) != (w != 0))[0]
+    assert len(mism) <= 3 and set(np.unique(got).tolist()) <= {0, 1, 2}
