@@ -152,7 +152,7 @@ int main() {
     // the same noise stream again: seek back, apply on the stand-alone kernels
     g.seek(0);
     DeviceVec sym = m.modulate(tx);
-    g.apply(sym);
+    g.apply(sym, Compat::Corrected);             // compat=reference scales the noise twice (src/noise.rs:58)
     DeviceBits rx2(4096);
     m.demod_naive(sym, rx2, Compat::Corrected);
     if (rx2.to_host() != rx.to_host()) { std::printf("FAIL modem_fused vs stand-alone kernels\n"); return 1; }
@@ -200,10 +200,17 @@ int main() {
     size_t arg = 0;
     for (size_t i = 0; i < l.size(); ++i) if (l[i] > l[arg]) arg = i;
     if (arg != 512) { std::printf("FAIL spectrogram DC bin at %zu\n", arg); return 1; }
-    DeviceVec p(std::vector<cf32>(x.begin(), x.begin() + 1024)), q(std::vector<cf32>(x.begin(), x.begin() + 1024));
-    f.correlate(p, q, Scale::N());
-    const std::vector<cf32> corr = p.to_host();
-    for (size_t i = 1; i < corr.size(); ++i) if (std::abs(corr[i]) >= std::abs(corr[0])) { std::printf("FAIL correlator peak\n"); return 1; }
+    // benches/benches.rs:410-416: input.vec_rfft(SN).vec_mul(&sig).vec_rifft(SN); a flat spectrum of 2 doubles the frame
+    DeviceVec p(std::vector<cf32>(x.begin(), x.begin() + 1024)), flat(rep({2, 0}, 1024));
+    f.correlate(p, flat, Scale::SN());
+    std::vector<cf32> twice(x.begin(), x.begin() + 1024);
+    for (auto& e : twice) e *= 2.0f;
+    {
+      double err = 0, ref = 0;
+      const std::vector<cf32> got = p.to_host();
+      for (size_t i = 0; i < got.size(); ++i) { err += std::norm(got[i] - twice[i]); ref += std::norm(twice[i]); }
+      if (!(err <= 1e-10 * ref)) { std::printf("FAIL correlator round trip: %g\n", err / ref); return 1; }
+    }
     if (version().empty() || device_count() < 1 || sm_count() < 1 || launch_count() == 0) { std::printf("FAIL runtime info\n"); return 1; }
   }
   sync();
