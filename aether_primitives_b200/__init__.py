@@ -7,16 +7,16 @@ the C ABI in include/aether_b200.h; there is no CPU fallback.
 """
 from . import _lib
 from ._lib import AeError, COMPAT_REFERENCE, COMPAT_CORRECTED
-from .runtime import init, sync, set_stream, device_count, launch_count, sm_count, use_torch_stream, Graph
+from .runtime import init, sync, set_stream, device_count, launch_count, sm_count, use_torch_stream, Graph, PinnedBuf
 from .vecops import DeviceVec, DeviceBits
 from .fft import Scale, Cfft
 from .fir import Fir
-from . import sampling, modulation, noise, sequence, chain, stats, spectral, util
+from . import sampling, modulation, noise, sequence, chain, stats, spectral, util, pipeline, pool
 
 cf32 = "complex64"  # numpy dtype of the reference's cf32 (src/lib.rs:12)
 
 __all__ = [
     "AeError", "COMPAT_REFERENCE", "COMPAT_CORRECTED", "init", "sync", "set_stream", "device_count",
-    "launch_count", "sm_count", "use_torch_stream", "Graph", "DeviceVec", "DeviceBits", "Scale", "Cfft", "Fir",
-    "sampling", "modulation", "noise", "sequence", "chain", "stats", "spectral", "util", "cf32",
+    "launch_count", "sm_count", "use_torch_stream", "Graph", "PinnedBuf", "DeviceVec", "DeviceBits", "Scale", "Cfft", "Fir",
+    "sampling", "modulation", "noise", "sequence", "chain", "stats", "spectral", "util", "pipeline", "pool", "cf32",
 ]

@@ -157,6 +157,18 @@ _SIGS = {
     "ae_pipe_recv": (None, [_P, C.POINTER(_P)]),
     "ae_pipe_in_flight": (_SZ, [_P]),
     "ae_pipe_report": (None, [_P, C.POINTER(PipeStage), _I]),
+    "ae_pipeline_create": (None, [_I, C.POINTER(_P)]),
+    "ae_pipeline_add_stage": (None, [_P, C.c_char_p, _P, _P]),
+    "ae_pipeline_send": (None, [_P, _P]),
+    "ae_pipeline_recv": (None, [_P, C.POINTER(_P)]),
+    "ae_pipeline_in_flight": (_SZ, [_P]),
+    "ae_pipeline_stages": (_SZ, [_P]),
+    "ae_pipeline_report": (None, [_P, C.POINTER(PipeStage), _SZ, _I]),
+    "ae_pipeline_destroy": (None, [_P]),
+    "ae_vec_upload_async": (None, [_P, _P, _SZ]),
+    "ae_vec_download_async": (None, [_P, _P, _SZ]),
+    "ae_bits_upload_async": (None, [_P, _P, _SZ]),
+    "ae_bits_download_async": (None, [_P, _P, _SZ]),
     "ae_graph_begin": (None, []),
     "ae_graph_end": (None, [C.POINTER(_P)]),
     "ae_graph_launch": (None, [_P]),

@@ -561,6 +561,22 @@ ae_status ae_vec_upload(ae_vec* v, const ae_cf32* host, size_t n) {
   }
   return AE_OK;
 }
+ae_status ae_vec_upload_async(ae_vec* v, const ae_cf32* host, size_t n) {
+  if (!v || (!host && n)) return fail(AE_EARG, "null");
+  if (n != v->len) return fail(AE_ELEN, "Vectors must have same length");
+  cudaSetDevice(v->c->dev);
+  TRY(before_write(v));
+  if (n) CK(cudaMemcpyAsync(vptr(v), host, n * sizeof(float2), cudaMemcpyHostToDevice, v->c->stream));
+  return AE_OK;
+}
+ae_status ae_vec_download_async(ae_vec* v, ae_cf32* host, size_t n) {
+  if (!v || (!host && n)) return fail(AE_EARG, "null");
+  if (n != v->len) return fail(AE_ELEN, "Vectors must have same length");
+  cudaSetDevice(v->c->dev);
+  TRY(before_read(v));
+  if (n) CK(cudaMemcpyAsync(host, vptr(v), n * sizeof(float2), cudaMemcpyDeviceToHost, v->c->stream));
+  return AE_OK;
+}
 ae_status ae_vec_download(ae_vec* v, ae_cf32* host, size_t n) {
   if (!v || (!host && n)) return fail(AE_EARG, "null");
   if (n != v->len) return fail(AE_ELEN, "Vectors must have same length");
@@ -662,6 +678,20 @@ ae_status ae_bits_upload(ae_bits* b, const uint8_t* host, size_t n) {
     CK(cudaMemcpyAsync(bptr(b), host, n, cudaMemcpyHostToDevice, b->c->stream));
     CK(cudaStreamSynchronize(b->c->stream));
   }
+  return AE_OK;
+}
+ae_status ae_bits_upload_async(ae_bits* b, const uint8_t* host, size_t n) {
+  if (!b || (!host && n)) return fail(AE_EARG, "null");
+  if (n != b->len) return fail(AE_ELEN, "Vectors must have same length");
+  cudaSetDevice(b->c->dev);
+  if (n) CK(cudaMemcpyAsync(bptr(b), host, n, cudaMemcpyHostToDevice, b->c->stream));
+  return AE_OK;
+}
+ae_status ae_bits_download_async(ae_bits* b, uint8_t* host, size_t n) {
+  if (!b || (!host && n)) return fail(AE_EARG, "null");
+  if (n != b->len) return fail(AE_ELEN, "Vectors must have same length");
+  cudaSetDevice(b->c->dev);
+  if (n) CK(cudaMemcpyAsync(host, bptr(b), n, cudaMemcpyDeviceToHost, b->c->stream));
   return AE_OK;
 }
 ae_status ae_bits_download(ae_bits* b, uint8_t* host, size_t n) {
@@ -1950,6 +1980,203 @@ ae_status ae_pipe_report(ae_pipe* p, ae_pipe_stage stages[3], int reset) {
   return AE_OK;
 }
 
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// General stage pipeline (src/pipeline.rs:26-137): a CUDA stream per stage instead of a thread, events
+// instead of channels.  Every stage's op runs on the calling thread inside ae_pipeline_send and only QUEUES
+// work: while it runs, the context stream is the stage's stream.
+// -------------------------------------------------------------------------------------------------
+struct FlowStage {
+  std::string name;
+  ae_stage_fn op = nullptr;
+  void* user = nullptr;
+  cudaStream_t st = nullptr;
+  std::vector<cudaEvent_t> ev0, ev1;    // per slot: before / after the stage's work for the item in that slot
+  double active_ms = 0, last_end_ms = 0;
+};
+struct ae_pipeline {
+  Ctx* c = nullptr;
+  int depth = 0;
+  std::vector<FlowStage> stages;
+  std::vector<void*> item;              // per slot
+  std::vector<char> busy;
+  std::vector<void*> done;              // retired items not yet handed out (FIFO)
+  size_t head = 0, tail = 0;
+  cudaEvent_t t0 = nullptr, fence = nullptr;
+  double window_end_ms = 0;
+  uint64_t processed = 0;
+  bool sent_any = false;
+};
+
+namespace {
+ae_status flush_all_pending(Ctx* c) {
+  std::vector<ae_vec*> snap = c->pending;
+  for (ae_vec* v : snap) TRY(flush_vec(v));
+  return AE_OK;
+}
+ae_status flow_retire(ae_pipeline* p, size_t slot) {
+  FlowStage& last = p->stages.back();
+  CK(cudaEventSynchronize(last.ev1[slot]));
+  float t_end = 0;
+  for (FlowStage& s : p->stages) {
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, p->t0, s.ev0[slot]));
+    CK(cudaEventElapsedTime(&b, p->t0, s.ev1[slot]));
+    const double start = std::max((double)a, s.last_end_ms), end = b;
+    if (end > start) s.active_ms += end - start;
+    s.last_end_ms = std::max(s.last_end_ms, end);
+    t_end = std::max(t_end, b);
+  }
+  p->window_end_ms = std::max(p->window_end_ms, (double)t_end);
+  p->processed += 1;
+  p->busy[slot] = 0;
+  p->done.push_back(p->item[slot]);
+  p->tail += 1;
+  return AE_OK;
+}
+}  // namespace
+
+extern "C" {
+ae_status ae_pipeline_create(int depth, ae_pipeline** out) {
+  if (!out) return fail(AE_EARG, "null");
+  if (depth < 1 || depth > 64) return fail(AE_EARG, "ae_pipeline_create: depth must be in 1..64");
+  Ctx* c;
+  TRY(get_ctx(&c));
+  ae_pipeline* p = new ae_pipeline;
+  p->c = c;
+  p->depth = depth;
+  p->item.assign((size_t)depth, nullptr);
+  p->busy.assign((size_t)depth, 0);
+  if (cudaEventCreate(&p->t0) != cudaSuccess || cudaEventCreateWithFlags(&p->fence, cudaEventDisableTiming) != cudaSuccess) {
+    ae_pipeline_destroy(p);
+    return fail(AE_ECUDA, "ae_pipeline_create: cudaEventCreate failed");
+  }
+  *out = p;
+  return AE_OK;
+}
+ae_status ae_pipeline_add_stage(ae_pipeline* p, const char* name, ae_stage_fn op, void* user) {
+  if (!p || !op) return fail(AE_EARG, "null");
+  if (p->sent_any) return fail(AE_EARG, "ae_pipeline_add_stage: the pipeline is already running");
+  cudaSetDevice(p->c->dev);
+  FlowStage s;
+  s.name = name ? name : "";
+  s.op = op;
+  s.user = user;
+  CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+  for (int i = 0; i < p->depth; ++i) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
+      if (a) cudaEventDestroy(a);
+      for (cudaEvent_t e : s.ev0) cudaEventDestroy(e);
+      for (cudaEvent_t e : s.ev1) cudaEventDestroy(e);
+      cudaStreamDestroy(s.st);
+      return fail(AE_ECUDA, "ae_pipeline_add_stage: cudaEventCreate failed");
+    }
+    s.ev0.push_back(a);
+    s.ev1.push_back(b);
+  }
+  p->stages.push_back(std::move(s));
+  return AE_OK;
+}
+ae_status ae_pipeline_send(ae_pipeline* p, void* item) {
+  if (!p) return fail(AE_EARG, "null");
+  if (p->stages.empty()) return fail(AE_EARG, "ae_pipeline_send: no stages");
+  Ctx* c = p->c;
+  cudaSetDevice(c->dev);
+  const size_t slot = p->head % (size_t)p->depth;
+  if (p->busy[slot]) TRY(flow_retire(p, slot));         // `depth` items in flight: wait for the oldest one
+  // whatever the caller queued on the context stream so far (recorded VecOps included) happens before the first stage
+  TRY(flush_all_pending(c));
+  cudaStream_t user_stream = c->stream;
+  if (!p->sent_any) {
+    CK(cudaEventRecord(p->t0, user_stream));
+    p->sent_any = true;
+  }
+  CK(cudaEventRecord(p->fence, user_stream));
+  CK(cudaStreamWaitEvent(p->stages[0].st, p->fence, 0));
+  if (p->head == 0) CK(cudaStreamWaitEvent(p->stages[0].st, p->t0, 0));
+  ae_status st = AE_OK;
+  for (size_t k = 0; k < p->stages.size() && st == AE_OK; ++k) {
+    FlowStage& s = p->stages[k];
+    cudaError_t e = cudaSuccess;
+    if (k > 0) e = cudaStreamWaitEvent(s.st, p->stages[k - 1].ev1[slot], 0);
+    if (e == cudaSuccess) e = cudaEventRecord(s.ev0[slot], s.st);
+    if (e != cudaSuccess) { st = fail(AE_ECUDA, std::string(cudaGetErrorString(e)) + " in ae_pipeline_send"); break; }
+    c->stream = s.st;                                    // the stage's "thread"
+    st = s.op(s.user, slot, item);
+    if (st == AE_OK) st = flush_all_pending(c);          // VecOps the stage recorded run on ITS stream
+    c->stream = user_stream;
+    e = cudaEventRecord(s.ev1[slot], s.st);
+    if (st == AE_OK && e != cudaSuccess) st = fail(AE_ECUDA, std::string(cudaGetErrorString(e)) + " in ae_pipeline_send");
+  }
+  if (st != AE_OK) {
+    // a failed stage leaves the item half processed: drain and report; the item is not in flight
+    for (FlowStage& s : p->stages) cudaStreamSynchronize(s.st);
+    return st;
+  }
+  p->item[slot] = item;
+  p->busy[slot] = 1;
+  p->head += 1;
+  return AE_OK;
+}
+ae_status ae_pipeline_recv(ae_pipeline* p, void** item_done) {
+  if (!p || !item_done) return fail(AE_EARG, "null");
+  cudaSetDevice(p->c->dev);
+  if (p->done.empty()) {
+    if (p->tail == p->head) return fail(AE_EARG, "ae_pipeline_recv: nothing in flight");
+    TRY(flow_retire(p, p->tail % (size_t)p->depth));
+  }
+  *item_done = p->done.front();
+  p->done.erase(p->done.begin());
+  return AE_OK;
+}
+size_t ae_pipeline_in_flight(const ae_pipeline* p) { return p ? (p->head - p->tail) + p->done.size() : 0; }
+size_t ae_pipeline_stages(const ae_pipeline* p) { return p ? p->stages.size() : 0; }
+ae_status ae_pipeline_report(ae_pipeline* p, ae_pipe_stage* stages, size_t n_stages, int reset) {
+  if (!p || (!stages && n_stages)) return fail(AE_EARG, "null");
+  if (n_stages < p->stages.size()) return fail(AE_ELEN, "ae_pipeline_report: room for every stage is required");
+  for (size_t k = 0; k < p->stages.size(); ++k) {
+    ae_pipe_stage& r = stages[k];
+    memset(&r, 0, sizeof(r));
+    snprintf(r.name, sizeof(r.name), "%s", p->stages[k].name.c_str());
+    r.processed = p->processed;
+    r.active_ms = p->stages[k].active_ms;
+    r.elapsed_ms = p->window_end_ms;
+    r.per_second = p->window_end_ms > 0 ? p->processed / p->window_end_ms * 1e3 : 0.0;
+    r.utilisation_pct = p->window_end_ms > 0 ? 100.0 * p->stages[k].active_ms / p->window_end_ms : 0.0;
+  }
+  if (reset) {
+    if (p->tail != p->head) return fail(AE_EARG, "ae_pipeline_report(reset): items still in flight");
+    cudaSetDevice(p->c->dev);
+    for (FlowStage& s : p->stages) {
+      CK(cudaStreamSynchronize(s.st));
+      s.active_ms = s.last_end_ms = 0;
+    }
+    CK(cudaEventRecord(p->t0, p->c->stream));
+    CK(cudaStreamWaitEvent(p->stages.empty() ? p->c->stream : p->stages[0].st, p->t0, 0));
+    p->window_end_ms = 0;
+    p->processed = 0;
+  }
+  return AE_OK;
+}
+ae_status ae_pipeline_destroy(ae_pipeline* p) {
+  if (!p) return AE_OK;
+  cudaSetDevice(p->c->dev);
+  for (FlowStage& s : p->stages) {
+    if (s.st) cudaStreamSynchronize(s.st);
+    for (cudaEvent_t e : s.ev0) cudaEventDestroy(e);
+    for (cudaEvent_t e : s.ev1) cudaEventDestroy(e);
+    if (s.st) cudaStreamDestroy(s.st);
+  }
+  if (p->t0) cudaEventDestroy(p->t0);
+  if (p->fence) cudaEventDestroy(p->fence);
+  delete p;
+  return AE_OK;
+}
+}  // extern "C"
+
+extern "C" {
 ae_status ae_ofdm_chain(size_t fft_len, size_t frames, uint64_t first_frame_id, float noise_power, uint64_t noise_seed,
                         int compat, ae_bits* tx_bits, ae_bits* rx_bits, ae_stats* d) {
   if (!ofdm_supported(fft_len)) return fail(AE_EARG, "ofdm chain supports power-of-two FFT lengths 512..4096");

@@ -83,3 +83,35 @@ class Graph:
             self.close()
         except Exception:
             pass
+
+
+class PinnedBuf:
+    """Page-locked host memory (`ae_host_alloc`) viewed as a numpy array: the staging buffers of the pipeline stages
+    and of the *_host entry points (pageable memory makes every "async" copy synchronous)."""
+
+    def __init__(self, n: int, dtype="complex64"):
+        import numpy as np
+
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(n) * self.dtype.itemsize
+        p = C.c_void_p()
+        call("ae_host_alloc", max(self.nbytes, 1), C.byref(p))
+        self._p = p
+        raw = (C.c_uint8 * max(self.nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(raw, dtype=self.dtype, count=int(n))
+
+    @property
+    def ptr(self) -> int:
+        return self._p.value or 0
+
+    def close(self) -> None:
+        if self._p:
+            self.array = None
+            lib().ae_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

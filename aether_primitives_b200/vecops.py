@@ -61,6 +61,15 @@ class DeviceBits:
         call("ae_bits_device_ptr", self._h, C.byref(p))
         return p.value or 0
 
+    def upload_async(self, host_ptr: int, n: int) -> "DeviceBits":
+        call("ae_bits_upload_async", self._h, C.c_void_p(host_ptr), n)
+        return self
+
+    def download_async(self, host_ptr: int, n: int) -> "DeviceBits":
+        """stream-ordered D2H copy into (pinned) host memory; valid once the pipeline item has been received"""
+        call("ae_bits_download_async", self._h, C.c_void_p(host_ptr), n)
+        return self
+
     def to_numpy(self) -> np.ndarray:
         out = np.empty(len(self), dtype=np.uint8)
         call("ae_bits_download", self._h, out.ctypes.data_as(C.c_void_p), out.size)
@@ -183,6 +192,15 @@ class DeviceVec:
     def upload(self, a) -> "DeviceVec":
         a = np.ascontiguousarray(a, dtype=np.complex64)
         call("ae_vec_upload", self._h, a.ctypes.data_as(C.c_void_p), a.size)
+        return self
+
+    def upload_async(self, host_ptr: int, n: int) -> "DeviceVec":
+        """stream-ordered H2D copy of n cf32 from (pinned) host memory; no synchronisation (pipeline stages)"""
+        call("ae_vec_upload_async", self._h, C.c_void_p(host_ptr), n)
+        return self
+
+    def download_async(self, host_ptr: int, n: int) -> "DeviceVec":
+        call("ae_vec_download_async", self._h, C.c_void_p(host_ptr), n)
         return self
 
     def to_numpy(self) -> np.ndarray:

@@ -525,6 +525,64 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         e2e["concurrent_copy_yardstick_Gsamples/s"] = yard
         e2e["frac_of_concurrent_yardstick"] = e2e["value"] / yard
         del d_tmp, d_out_tmp, h_out2
+        # the same job through the GENERAL stage pipeline (ae_pipeline_*: pipeline.rs / pool.rs of the reference on CUDA
+        # streams): three user-defined stages over pooled device blocks, fed with 64 MiB slices of the same pinned buffers
+        try:
+            chunk_frames = min(8192, e2e_frames)
+            cs = chunk_frames * FFT_LEN
+            n_chunks = ne // cs
+
+            class _Blk:
+                def __init__(self):
+                    self.d = ae.DeviceVec.zeros(cs)
+                    self.bits = ae.DeviceBits.zeros(2 * cs)
+                    self.off = 0
+
+            blk_pool = ae.pool.make(0, _Blk, lambda b: None)
+            hin_p, hout_p = h_in.data_ptr(), h_out.data_ptr()
+
+            def st_h2d(e):
+                e.val.d.upload_async(hin_p + 8 * e.val.off, cs)
+                return e
+
+            def st_chain(e):
+                chain.run(e.val.d, e.val.bits)
+                return e
+
+            def st_d2h(e):
+                e.val.bits.download_async(hout_p + 2 * e.val.off, 2 * cs)
+                return e
+
+            h_out.zero_()
+            tx, rx = ae.pipeline.Pipeline.new("h2d", st_h2d, depth=3).add_stage("fft-fir-demod", st_chain).add_stage("d2h", st_d2h).finish()
+
+            def gp_step():
+                for ci in range(n_chunks):
+                    if rx.in_flight() == 3:
+                        rx.recv().release()
+                    e = blk_pool.take_or_make()
+                    e.val.off = ci * cs
+                    tx.send(e)
+                while rx.in_flight():
+                    rx.recv().release()
+
+            gp_step()
+            rx.report(reset=True)
+            barrier()
+            tg0 = time.perf_counter()
+            for _ in range(3):
+                gp_step()
+            tg = torch.tensor([time.perf_counter() - tg0], dtype=torch.float64, device="cuda")
+            if dist:
+                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            rep = rx.report()
+            e2e["general_pipeline"] = {"Gsamples/s": world * n_chunks * cs * 3 / float(tg.item()) / 1e9, "chunk_frames": chunk_frames,
+                                       "depth": 3, "matches_device_path": bool(torch.equal(h_out[: 2 * n_chunks * cs].cuda(), bits[: 2 * n_chunks * cs])),
+                                       "stage_utilisation_pct": {r["name"]: round(r["utilisation_pct"], 1) for r in rep},
+                                       "note": "ae_pipeline_*: user stages h2d / chain / d2h on three streams, pooled device blocks, host closures in Python"}
+            del tx, rx, blk_pool
+        except Exception as ex:
+            e2e["general_pipeline"] = {"error": repr(ex)}
         del h_in, h_out
         try:
             os.sched_setaffinity(0, affinity0)       # the CPU baseline below uses every host core

@@ -269,6 +269,33 @@ ae_status ae_pipe_recv(ae_pipe* p, uint8_t** host_bits_done);
 size_t    ae_pipe_in_flight(const ae_pipe* p);      /* sent and not yet received */
 ae_status ae_pipe_report(ae_pipe* p, ae_pipe_stage stages[3], int reset);
 
+/* General form (src/pipeline.rs:26-137: pipeline::new(name, op).add_stage(name, op)...finish()): any number of named
+ * stages, each with its own CUDA stream in place of the reference's thread and CUDA events in place of its channels.
+ * ae_pipeline_send(item) calls every stage's `op` once, in order, on the calling thread; while `op` runs, the library's
+ * context stream IS that stage's stream, so whatever the stage does through this API (kernels, ae_*_async copies) is
+ * queued there and `op` returns without waiting.  Stage k of item i therefore overlaps stage k+1 of item i-1, exactly like
+ * the reference's stage threads; items leave in the order they entered.  At most `depth` items are in flight (send waits
+ * for the oldest one otherwise); ae_pipeline_recv returns the next finished item, waiting for its last stage.  The report
+ * is the reference's per-stage line (:93-107).  Rules: a handle with internal scratch (FFT plan, FIR state, Awgn stream)
+ * belongs to ONE stage; an `op` must not call anything that synchronises (downloads, ae_sync, ae_stats_read) nor
+ * ae_set_stream; buffers an item carries are reused only after it has been received (take them from a pool). */
+typedef struct ae_pipeline ae_pipeline;
+typedef ae_status (*ae_stage_fn)(void* user, size_t slot /* 0..depth-1, stable while the item is in flight */, void* item);
+ae_status ae_pipeline_create(int depth, ae_pipeline** out);
+ae_status ae_pipeline_add_stage(ae_pipeline* p, const char* name, ae_stage_fn op, void* user);
+ae_status ae_pipeline_send(ae_pipeline* p, void* item);
+ae_status ae_pipeline_recv(ae_pipeline* p, void** item_done);
+size_t    ae_pipeline_in_flight(const ae_pipeline* p);
+size_t    ae_pipeline_stages(const ae_pipeline* p);
+ae_status ae_pipeline_report(ae_pipeline* p, ae_pipe_stage* stages, size_t n_stages, int reset);
+ae_status ae_pipeline_destroy(ae_pipeline* p);       /* waits for everything in flight */
+/* stream-ordered copies for pipeline stages: no synchronisation; `host` must be pinned (ae_host_alloc) to overlap and
+ * must stay valid until the item is received */
+ae_status ae_vec_upload_async(ae_vec* v, const ae_cf32* host, size_t n);
+ae_status ae_vec_download_async(ae_vec* v, ae_cf32* host, size_t n);
+ae_status ae_bits_upload_async(ae_bits* b, const uint8_t* host, size_t n);
+ae_status ae_bits_download_async(ae_bits* b, uint8_t* host, size_t n);
+
 /* ---- CUDA graphs: launch-bound shapes (examples/modem.rs runs 1M symbols, a ~4 us kernel) ----------
  * Between ae_graph_begin and ae_graph_end every launch the library makes on the context stream is RECORDED instead of
  * run (cudaStreamBeginCapture); ae_graph_launch replays the whole recording with one driver call.  Rules of stream

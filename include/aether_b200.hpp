@@ -19,9 +19,15 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <exception>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <optional>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -88,6 +94,8 @@ class DeviceBits {
   size_t capacity() const { return ae_bits_capacity(h_); }
   void* device_ptr() const { void* q = nullptr; check(ae_bits_device_ptr(h_, &q)); return q; }
   void clear() { check(ae_bits_set_len(h_, 0)); }
+  void upload_async(const uint8_t* host, size_t n) { check(ae_bits_upload_async(h_, host, n)); }
+  void download_async(uint8_t* host, size_t n) const { check(ae_bits_download_async(h_, host, n)); }
   std::vector<uint8_t> to_host() const {
     std::vector<uint8_t> v(len());
     check(ae_bits_download(h_, v.data(), v.size()));
@@ -142,6 +150,9 @@ class DeviceVec {
   /// the recorded VecOps chain runs when the data is needed; flush() runs it now
   size_t pending_ops() const { return ae_vec_pending_ops(h_); }
   void flush() { check(ae_vec_flush(h_)); }
+  /// stream-ordered copies for pipeline stages: no synchronisation, host memory pinned and valid until the item is received
+  void upload_async(const cf32* host, size_t n) { check(ae_vec_upload_async(h_, reinterpret_cast<const ae_cf32*>(host), n)); }
+  void download_async(cf32* host, size_t n) const { check(ae_vec_download_async(h_, reinterpret_cast<ae_cf32*>(host), n)); }
   std::vector<cf32> to_host() const {
     std::vector<cf32> v(len());
     check(ae_vec_download(h_, reinterpret_cast<ae_cf32*>(v.data()), v.size()));
@@ -217,7 +228,8 @@ class PinnedBuf {
  public:
   explicit PinnedBuf(size_t n) : n_(n) { void* q = nullptr; check(ae_host_alloc(n * sizeof(T), &q)); p_ = static_cast<T*>(q); }
   PinnedBuf(const PinnedBuf&) = delete;
-  ~PinnedBuf() { ae_host_free(p_); }
+  PinnedBuf(PinnedBuf&& o) noexcept : p_(std::exchange(o.p_, nullptr)), n_(std::exchange(o.n_, 0)) {}
+  ~PinnedBuf() { if (p_) ae_host_free(p_); }
   T* data() { return p_; }
   const T* data() const { return p_; }
   size_t size() const { return n_; }
@@ -529,6 +541,196 @@ class ChainPipeline {
  private:
   ae_pipe* h_ = nullptr;
 };
+
+/// pool::{make, Pool, Elem} (src/pool.rs:43-250): reusable, expensive-to-make objects behind guards — here pinned host
+/// buffers and device vectors.  take() is the bounded use (nothing when the pool is empty), take_or_make() grows it; the
+/// guard resets its element and returns it to the pool when it goes out of scope.
+namespace pool {
+template <class T>
+class Pool;
+namespace detail {
+template <class T>
+struct Inner {
+  std::mutex mu;
+  std::vector<T> elems;
+  std::function<T()> maker;
+  std::function<void(T&)> resetter;
+  size_t cap = 0;
+};
+}  // namespace detail
+template <class T>
+class Elem {
+ public:
+  Elem(std::shared_ptr<detail::Inner<T>> pool, T val) : pool_(std::move(pool)), val_(std::move(val)), live_(true) {}
+  Elem(const Elem&) = delete;
+  Elem(Elem&& o) noexcept : pool_(std::move(o.pool_)), val_(std::move(o.val_)), live_(std::exchange(o.live_, false)) {}
+  ~Elem() {
+    if (!live_) return;
+    pool_->resetter(val_);
+    std::lock_guard<std::mutex> lk(pool_->mu);
+    pool_->elems.push_back(std::move(val_));
+  }
+  T& operator*() { return val_; }
+  T* operator->() { return &val_; }
+
+ private:
+  std::shared_ptr<detail::Inner<T>> pool_;
+  T val_;
+  bool live_;
+};
+template <class T>
+class Pool {
+ public:
+  explicit Pool(std::shared_ptr<detail::Inner<T>> inner) : inner_(std::move(inner)) {}
+  Pool clone() const { return Pool(inner_); }
+  std::optional<Elem<T>> take() {
+    std::lock_guard<std::mutex> lk(inner_->mu);
+    if (inner_->elems.empty()) return std::nullopt;
+    T v = std::move(inner_->elems.back());
+    inner_->elems.pop_back();
+    return Elem<T>(inner_, std::move(v));
+  }
+  Elem<T> take_or_make() {
+    {
+      std::lock_guard<std::mutex> lk(inner_->mu);
+      if (!inner_->elems.empty()) {
+        T v = std::move(inner_->elems.back());
+        inner_->elems.pop_back();
+        return Elem<T>(inner_, std::move(v));
+      }
+      inner_->cap += 1;
+    }
+    return Elem<T>(inner_, inner_->maker());
+  }
+  size_t len() const { std::lock_guard<std::mutex> lk(inner_->mu); return inner_->elems.size(); }
+  bool is_empty() const { return len() == 0; }
+  size_t cap() const { std::lock_guard<std::mutex> lk(inner_->mu); return inner_->cap; }
+
+ private:
+  std::shared_ptr<detail::Inner<T>> inner_;
+};
+template <class T>
+Pool<T> make(size_t initial_len, std::function<T()> maker, std::function<void(T&)> resetter) {
+  auto inner = std::make_shared<detail::Inner<T>>();
+  inner->maker = std::move(maker);
+  inner->resetter = std::move(resetter);
+  for (size_t i = 0; i < initial_len; ++i) {
+    T e = inner->maker();
+    inner->resetter(e);
+    inner->elems.push_back(std::move(e));
+  }
+  inner->cap = inner->elems.size();
+  return Pool<T>(std::move(inner));
+}
+}  // namespace pool
+
+/// pipeline::{new, Pipeline::add_stage, finish} (src/pipeline.rs:26-137) over ae_pipeline_*: a CUDA stream per stage instead
+/// of a thread, CUDA events instead of channels.  Sender::send(item) runs every stage's closure once, in order, on the
+/// calling thread; the closures only queue work (kernels, *_async copies) — while one runs, everything the library launches
+/// goes to that stage's stream, so stage k of item i overlaps stage k+1 of item i-1.  Receiver::recv() returns finished
+/// items in order; report() is the line the reference's stage threads print.
+namespace pipeline {
+namespace detail {
+struct Holder { virtual ~Holder() = default; };
+template <class T>
+struct Value : Holder {
+  T v;
+  explicit Value(T x) : v(std::move(x)) {}
+};
+using Box = std::unique_ptr<Holder>;
+struct State;
+struct StageCtx { State* st; size_t index; };
+struct State {
+  ae_pipeline* h = nullptr;
+  std::vector<std::function<Box(Box)>> ops;
+  std::vector<std::unique_ptr<StageCtx>> ctx;
+  std::exception_ptr error;
+  ~State() { if (h) ae_pipeline_destroy(h); }
+  static ae_status tramp(void* user, size_t /*slot*/, void* item) {
+    auto* sc = static_cast<StageCtx*>(user);
+    auto* box = static_cast<Box*>(item);
+    try {
+      *box = sc->st->ops[sc->index](std::move(*box));
+      return AE_OK;
+    } catch (...) {                       // an exception must not unwind through the C frames
+      sc->st->error = std::current_exception();
+      return AE_EARG;
+    }
+  }
+  template <class In, class Out, class F>
+  void add(const char* name, F op) {
+    ops.push_back([op = std::move(op)](Box b) mutable -> Box {
+      auto* in = static_cast<Value<In>*>(b.get());
+      return Box(new Value<Out>(op(std::move(in->v))));
+    });
+    ctx.push_back(std::make_unique<StageCtx>(StageCtx{this, ops.size() - 1}));
+    check(ae_pipeline_add_stage(h, name, &State::tramp, ctx.back().get()));
+  }
+};
+}  // namespace detail
+
+template <class I>
+class Sender {
+ public:
+  explicit Sender(std::shared_ptr<detail::State> s) : s_(std::move(s)) {}
+  void send(I item) {
+    auto* box = new detail::Box(new detail::Value<I>(std::move(item)));
+    const ae_status st = ae_pipeline_send(s_->h, box);
+    if (st != AE_OK) {
+      delete box;
+      if (s_->error) std::rethrow_exception(std::exchange(s_->error, nullptr));
+      check(st);
+    }
+  }
+
+ private:
+  std::shared_ptr<detail::State> s_;
+};
+template <class O>
+class Receiver {
+ public:
+  explicit Receiver(std::shared_ptr<detail::State> s) : s_(std::move(s)) {}
+  O recv() {
+    void* p = nullptr;
+    check(ae_pipeline_recv(s_->h, &p));
+    std::unique_ptr<detail::Box> box(static_cast<detail::Box*>(p));
+    return std::move(static_cast<detail::Value<O>*>(box->get())->v);
+  }
+  size_t in_flight() const { return ae_pipeline_in_flight(s_->h); }
+  std::vector<ae_pipe_stage> report(bool reset = false) {
+    std::vector<ae_pipe_stage> st(ae_pipeline_stages(s_->h));
+    check(ae_pipeline_report(s_->h, st.data(), st.size(), reset));
+    return st;
+  }
+
+ private:
+  std::shared_ptr<detail::State> s_;
+};
+template <class I, class O>
+class Pipeline {
+ public:
+  explicit Pipeline(std::shared_ptr<detail::State> s) : s_(std::move(s)) {}
+  /// add another stage: op maps what the previous stage returned to what the next one gets (FnMut(O) -> U)
+  template <class F, class U = std::invoke_result_t<F, O>>
+  Pipeline<I, U> add_stage(const char* name, F op) {
+    s_->template add<O, U>(name, std::move(op));
+    return Pipeline<I, U>(std::move(s_));
+  }
+  std::pair<Sender<I>, Receiver<O>> finish() { return {Sender<I>(s_), Receiver<O>(s_)}; }
+
+ private:
+  std::shared_ptr<detail::State> s_;
+};
+/// pipeline::new(name, op): `depth` items may be in flight (the reference's channels are unbounded; here the device
+/// buffers an item carries bound it — send() waits for the oldest item when `depth` are in flight)
+template <class I, class F, class O = std::invoke_result_t<F, I>>
+Pipeline<I, O> new_(const char* name, F op, int depth = 3) {
+  auto s = std::make_shared<detail::State>();
+  check(ae_pipeline_create(depth, &s->h));
+  s->template add<I, O>(name, std::move(op));
+  return Pipeline<I, O>(std::move(s));
+}
+}  // namespace pipeline
 
 /// util::DB (src/util/mod.rs:11-46): a value in decibel; DB::from(ratio) = 10 log10(ratio) in f64
 struct DB {

@@ -445,3 +445,93 @@ pub mod chain {
     }
     impl<'a> Drop for Pipe<'a> { fn drop(&mut self) { unsafe { sys::ae_pipe_destroy(self.h); } } }
 }
+
+// ---------------------------------------------------------------- pipeline.rs on CUDA streams
+/// `pipeline::new(name, op).add_stage(name, op)....finish()` of the reference (src/pipeline.rs:26-137) with a CUDA stream
+/// per stage instead of a thread and CUDA events instead of channels.  `Sender::send` runs every stage's closure once, in
+/// order, on the calling thread; the closures only QUEUE work (kernels, `*_async` copies) — while one runs, everything the
+/// library launches goes to that stage's stream, so stage k of item i overlaps stage k+1 of item i-1 on the GPU.  Items
+/// come out of `Receiver::recv` in the order they went in.  The crate's own `pool::Pool<T>` feeds it unchanged
+/// (`T` = a struct of `PinnedBuf`s and `DeviceVec`s).
+pub mod pipeline {
+    use super::*;
+    use std::any::Any;
+    use std::cell::RefCell;
+    use std::rc::Rc;
+
+    type Boxed = Box<dyn Any>;
+    struct Stage { op: Box<dyn FnMut(Boxed) -> Boxed> }
+    struct State { h: *mut sys::ae_pipeline, stages: Vec<Box<RefCell<Stage>>> }
+    impl Drop for State { fn drop(&mut self) { unsafe { sys::ae_pipeline_destroy(self.h); } } }
+
+    extern "C" fn tramp(user: *mut c_void, _slot: usize, item: *mut c_void) -> sys::ae_status {
+        // user: the stage; item: a heap cell holding the travelling value
+        let stage = unsafe { &*(user as *const RefCell<Stage>) };
+        let cell = unsafe { &mut *(item as *mut Option<Boxed>) };
+        let v = cell.take().expect("pipeline item");
+        *cell = Some((stage.borrow_mut().op)(v));
+        sys::AE_OK
+    }
+
+    pub struct Pipeline<I, O> { st: Rc<RefCell<State>>, _m: std::marker::PhantomData<(I, O)> }
+    pub struct Sender<I> { st: Rc<RefCell<State>>, _m: std::marker::PhantomData<I> }
+    pub struct Receiver<O> { st: Rc<RefCell<State>>, _m: std::marker::PhantomData<O> }
+
+    fn push_stage<A: 'static, B: 'static>(st: &Rc<RefCell<State>>, name: &str, mut op: impl FnMut(A) -> B + 'static) {
+        let stage = Box::new(RefCell::new(Stage { op: Box::new(move |b: Boxed| -> Boxed { Box::new(op(*b.downcast::<A>().expect("stage input type"))) }) }));
+        let user = &*stage as *const RefCell<Stage> as *mut c_void;
+        let cname = CString::new(name).unwrap();
+        let mut s = st.borrow_mut();
+        unsafe { ck(sys::ae_pipeline_add_stage(s.h, cname.as_ptr(), tramp, user)) };
+        s.stages.push(stage);
+    }
+
+    /// `depth` items may be in flight (the reference's channels are unbounded; here the buffers an item carries bound it)
+    pub fn new<I: 'static, O: 'static>(name: &str, op: impl FnMut(I) -> O + 'static, depth: i32) -> Pipeline<I, O> {
+        let mut h = null_mut();
+        unsafe { ck(sys::ae_pipeline_create(depth, &mut h)) };
+        let st = Rc::new(RefCell::new(State { h, stages: Vec::new() }));
+        push_stage::<I, O>(&st, name, op);
+        Pipeline { st, _m: std::marker::PhantomData }
+    }
+    impl<I: 'static, O: 'static> Pipeline<I, O> {
+        pub fn add_stage<U: 'static>(self, name: &str, op: impl FnMut(O) -> U + 'static) -> Pipeline<I, U> {
+            push_stage::<O, U>(&self.st, name, op);
+            Pipeline { st: self.st, _m: std::marker::PhantomData }
+        }
+        pub fn finish(self) -> (Sender<I>, Receiver<O>) {
+            (Sender { st: self.st.clone(), _m: std::marker::PhantomData }, Receiver { st: self.st, _m: std::marker::PhantomData })
+        }
+    }
+    impl<I: 'static> Sender<I> {
+        pub fn send(&self, item: I) {
+            let cell: *mut Option<Boxed> = Box::into_raw(Box::new(Some(Box::new(item) as Boxed)));
+            let h = self.st.borrow().h;
+            unsafe { ck(sys::ae_pipeline_send(h, cell as *mut c_void)) }
+        }
+    }
+    impl<O: 'static> Receiver<O> {
+        pub fn recv(&self) -> O {
+            let mut p = null_mut();
+            let h = self.st.borrow().h;
+            unsafe { ck(sys::ae_pipeline_recv(h, &mut p)) };
+            let cell = unsafe { Box::from_raw(p as *mut Option<Boxed>) };
+            *cell.expect("pipeline item").downcast::<O>().expect("pipeline output type")
+        }
+        pub fn in_flight(&self) -> usize { unsafe { sys::ae_pipeline_in_flight(self.st.borrow().h) } }
+        /// per stage: processed, active time, rate, utilisation — what the reference's stage threads print (:93-107)
+        pub fn report(&self, reset: bool) -> Vec<sys::ae_pipe_stage> {
+            let h = self.st.borrow().h;
+            let n = unsafe { sys::ae_pipeline_stages(h) };
+            let mut st: Vec<sys::ae_pipe_stage> = Vec::with_capacity(n);
+            unsafe { ck(sys::ae_pipeline_report(h, st.as_mut_ptr(), n, reset as c_int)); st.set_len(n) };
+            st
+        }
+    }
+
+    /// stream-ordered copies for the stages: no synchronisation; `host` is pinned and stays valid until the item is received
+    pub unsafe fn upload_async(v: &mut DeviceVec, host: *const cf32, n: usize) { ck(sys::ae_vec_upload_async(v.h, host as *const _, n)) }
+    pub unsafe fn download_async(v: &mut DeviceVec, host: *mut cf32, n: usize) { ck(sys::ae_vec_download_async(v.h, host as *mut _, n)) }
+    pub unsafe fn upload_bits_async(b: &mut DeviceBits, host: *const u8, n: usize) { ck(sys::ae_bits_upload_async(b.h, host, n)) }
+    pub unsafe fn download_bits_async(b: &mut DeviceBits, host: *mut u8, n: usize) { ck(sys::ae_bits_download_async(b.h, host, n)) }
+}

@@ -213,6 +213,94 @@ int main() {
     }
     if (version().empty() || device_count() < 1 || sm_count() < 1 || launch_count() == 0) { std::printf("FAIL runtime info\n"); return 1; }
   }
+  {  // src/pool.rs:264-329: taking, resetting, taking_or_making
+    auto p = pool::make<std::vector<uint8_t>>(1, [] { std::vector<uint8_t> v; v.reserve(50); return v; }, [](std::vector<uint8_t>& o) { o.clear(); });
+    if (p.len() != 1 || p.cap() != 1) { std::printf("FAIL pool make\n"); return 1; }
+    {
+      auto c1 = p.take();
+      if (!c1 || p.len() != 0 || p.cap() != 1) { std::printf("FAIL pool: first checkout\n"); return 1; }
+      for (int x = 0; x < 50; ++x) (**c1).push_back((uint8_t)x);
+    }
+    if (p.len() != 1 || p.cap() != 1) { std::printf("FAIL pool: give back\n"); return 1; }
+    {
+      auto c1 = p.take();
+      auto c2 = p.take();
+      if (!c1 || c2 || !(**c1).empty()) { std::printf("FAIL pool: second / third checkout, resetter\n"); return 1; }
+    }
+    auto q = pool::make<std::vector<uint8_t>>(0, [] { return std::vector<uint8_t>(); }, [](std::vector<uint8_t>& o) { o.clear(); });
+    {
+      auto e1 = q.take_or_make();
+      if (q.len() != 0 || q.cap() != 1) { std::printf("FAIL pool: take_or_make 1\n"); return 1; }
+      auto e2 = q.clone().take_or_make();
+      if (q.len() != 0 || q.cap() != 2) { std::printf("FAIL pool: take_or_make 2\n"); return 1; }
+    }
+    if (q.len() != 2 || q.cap() != 2 || q.is_empty()) { std::printf("FAIL pool: both guards dropped\n"); return 1; }
+  }
+  {  // src/pipeline.rs: three stages (H2D copy, transform + VecOps + demod, D2H copy) on three streams, pooled pinned and
+     // device buffers travelling through them; results == the same calls made one by one, in order
+    struct Block {
+      PinnedBuf<cf32> h_in;
+      PinnedBuf<uint8_t> h_bits;
+      DeviceVec d;
+      DeviceBits bits;
+      int tag = -1;
+      explicit Block(size_t n) : h_in(n), h_bits(2 * n), d(n), bits(2 * n) {}
+    };
+    const size_t n = 1024, frames = 16, ns = n * frames, blocks = 6;
+    const int depth = 3;
+    auto blocks_pool = pool::make<Block>(0, [&] { return Block(ns); }, [](Block& b) { b.tag = -1; b.bits.clear(); });   // demod_naive appends
+    Cfft fft = Cfft::with_len(n);
+    Modulation q = qpsk();
+    DeviceVec w(rep({0.6f, 0.8f}, ns));
+    using Item = pool::Elem<Block>;
+    auto built = pipeline::new_<Item>("h2d", [&](Item e) { e->d.upload_async(e->h_in.data(), ns); return e; }, depth)
+                     .add_stage("fft-mul-demod", [&](Item e) {
+                       fft.ifwd(e->d, Scale::SN(), frames);
+                       e->d.vec_mul(w).vec_conj();
+                       q.demod_naive(e->d, e->bits);
+                       return e;
+                     })
+                     .add_stage("d2h", [&](Item e) { e->bits.download_async(e->h_bits.data(), 2 * ns); return e; })
+                     .finish();
+    auto& tx = built.first;
+    auto& rx = built.second;
+    std::vector<std::vector<cf32>> xs(blocks, std::vector<cf32>(ns));
+    uint32_t lcg = 4242;
+    for (auto& x : xs) for (auto& e : x) { lcg = lcg * 1664525u + 1013904223u; e = cf32((float)(lcg >> 8) / 8388608.f - 1.f, (float)(lcg & 0xffff) / 32768.f - 1.f); }
+    std::vector<std::pair<int, std::vector<uint8_t>>> got;
+    auto take_result = [&] {
+      Item e = rx.recv();
+      got.emplace_back(e->tag, std::vector<uint8_t>(e->h_bits.data(), e->h_bits.data() + 2 * ns));
+    };
+    for (size_t i = 0; i < blocks; ++i) {
+      if (rx.in_flight() == (size_t)depth) take_result();
+      Item e = blocks_pool.take_or_make();
+      e->tag = (int)i;
+      std::memcpy(e->h_in.data(), xs[i].data(), ns * sizeof(cf32));
+      tx.send(std::move(e));
+    }
+    while (rx.in_flight()) take_result();
+    if (blocks_pool.cap() > (size_t)depth || blocks_pool.len() != blocks_pool.cap()) { std::printf("FAIL pipeline: pool reuse\n"); return 1; }
+    for (size_t i = 0; i < blocks; ++i) {
+      if (got[i].first != (int)i) { std::printf("FAIL pipeline: order\n"); return 1; }
+      DeviceVec d(xs[i]);
+      fft.ifwd(d, Scale::SN(), frames);
+      d.vec_mul(w).vec_conj();
+      DeviceBits bits(2 * ns);
+      q.demod_naive(d, bits);
+      if (bits.to_host() != got[i].second) { std::printf("FAIL pipeline: block %zu differs from the serial calls\n", i); return 1; }
+    }
+    const auto rep3 = rx.report();
+    if (rep3.size() != 3 || std::string(rep3[1].name) != "fft-mul-demod" || rep3[0].processed != blocks || !(rep3[2].active_ms > 0)) {
+      std::printf("FAIL pipeline: report\n");
+      return 1;
+    }
+    // a throwing stage surfaces from send() and leaves nothing in flight
+    auto bad = pipeline::new_<int>("ok", [](int v) { return v + 1; }, 2).add_stage("boom", [](int) -> int { throw std::runtime_error("stage failed"); }).finish();
+    bool threw = false;
+    try { bad.first.send(1); } catch (const std::runtime_error&) { threw = true; }
+    if (!threw || bad.second.in_flight() != 0) { std::printf("FAIL pipeline: stage error\n"); return 1; }
+  }
   sync();
   std::printf("host mirror ok\n");
   return 0;

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_symbols():
     src = open(os.path.join(ROOT, "include", "aether_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ae_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(ae_[a-z0-9_]+)\s*\((?!\s*\*)", src)))      # not `ae_status (*ae_stage_fn)(...)`
 
 
 def test_library_exports_every_declared_symbol():

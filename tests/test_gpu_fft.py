@@ -179,10 +179,12 @@ def test_large_power_of_two_four_step(ae, n):
         assert same_bits(din.to_numpy(), got)
 
 
-@pytest.mark.parametrize("n", [6, 7, 11, 13, 14, 17, 34, 49, 77, 85, 91, 143, 169, 210, 289, 1001, 1536, 4199, 6000, 6144])
+@pytest.mark.parametrize("n", [6, 7, 11, 13, 14, 17, 18, 20, 24, 30, 34, 49, 60, 77, 85, 91, 96, 143, 169, 210, 289, 600, 1001, 1200, 1536,
+                               3000, 4199, 6000, 6144])
 def test_mixed_radix_lengths_with_ragged_frame_groups(ae, n):
-    """Any-length path: register butterflies for 2/3/4/5/7/8/11/13, per-output fallback for other primes
-    (17, 19), several frames per CTA — frame counts that do not fill the last CTA's slots, in place and
+    """Any-length path: register butterflies for 2/3/4/5/7/8/11/13 and the prime-factor composites 6/10/12 (5*2, 3*4, 3*2 are
+    merged: 18 = 6*3, 20 = 10*2, 24 = 12*2, 60 = 10*6, 600 = 10*10*6, 1200 = 10*10*12, 3000 = 3*10*10*10), per-output fallback
+    for other primes (17, 19), several frames per CTA — frame counts that do not fill the last CTA's slots, in place and
     out of place, both directions."""
     frames = 45 if n <= 1100 else 5
     x = rnd(n * frames, n)
