@@ -526,7 +526,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         e2e["frac_of_concurrent_yardstick"] = e2e["value"] / yard
         del d_tmp, d_out_tmp, h_out2
         # the same job through the GENERAL stage pipeline (ae_pipeline_*: pipeline.rs / pool.rs of the reference on CUDA
-        # streams): three user-defined stages over pooled device blocks, fed with 64 MiB slices of the same pinned buffers
+        # streams): three user-defined stages over pooled device blocks, fed with 64 MiB slices of the same pinned buffers.
+        # No collective inside the try: a rank that fails must not leave the others waiting.
+        gp, gp_secs = None, float("inf")
         try:
             chunk_frames = min(8192, e2e_frames)
             cs = chunk_frames * FFT_LEN
@@ -568,21 +570,24 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
             gp_step()
             rx.report(reset=True)
-            barrier()
             tg0 = time.perf_counter()
             for _ in range(3):
                 gp_step()
-            tg = torch.tensor([time.perf_counter() - tg0], dtype=torch.float64, device="cuda")
-            if dist:
-                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            gp_secs = time.perf_counter() - tg0
             rep = rx.report()
-            e2e["general_pipeline"] = {"Gsamples/s": world * n_chunks * cs * 3 / float(tg.item()) / 1e9, "chunk_frames": chunk_frames,
-                                       "depth": 3, "matches_device_path": bool(torch.equal(h_out[: 2 * n_chunks * cs].cuda(), bits[: 2 * n_chunks * cs])),
-                                       "stage_utilisation_pct": {r["name"]: round(r["utilisation_pct"], 1) for r in rep},
-                                       "note": "ae_pipeline_*: user stages h2d / chain / d2h on three streams, pooled device blocks, host closures in Python"}
+            gp = {"chunk_frames": chunk_frames, "depth": 3, "samples_per_rank": n_chunks * cs * 3,
+                  "matches_device_path": bool(torch.equal(h_out[: 2 * n_chunks * cs].cuda(), bits[: 2 * n_chunks * cs])),
+                  "stage_utilisation_pct": {r["name"]: round(r["utilisation_pct"], 1) for r in rep},
+                  "note": "ae_pipeline_*: user stages h2d / chain / d2h on three streams, pooled device blocks, host closures in Python"}
             del tx, rx, blk_pool
         except Exception as ex:
-            e2e["general_pipeline"] = {"error": repr(ex)}
+            gp = {"error": repr(ex)}
+        tg = torch.tensor([gp_secs], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        if "error" not in gp and float(tg.item()) != float("inf"):
+            gp["Gsamples/s"] = world * gp.pop("samples_per_rank") / float(tg.item()) / 1e9
+        e2e["general_pipeline"] = gp
         del h_in, h_out
         try:
             os.sched_setaffinity(0, affinity0)       # the CPU baseline below uses every host core
