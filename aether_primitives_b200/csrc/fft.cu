@@ -196,10 +196,11 @@ void launch_fft_pow2(const float2* in, float2* out, size_t n, size_t frames, con
 // A CTA owns CT adjacent columns; thread = (t, c) with c fastest, so every global access is a run of
 // CT contiguous cf32 per row.  W_N^e is formed from two 4096-entry tables, W^(e>>12 <<12) * W^(e&4095).
 // -------------------------------------------------------------------------------------------------
-template <int N1>
+constexpr int col_default_ct(int n1) { return n1 >= 4096 ? 4 : (n1 >= 1024 ? 8 : 16); }
+template <int N1, int CTV = col_default_ct(N1)>
 struct ColLaunch {
   static constexpr int T = FftCfg<N1>::T;
-  static constexpr int CT = N1 >= 4096 ? 4 : (N1 >= 1024 ? 8 : 16);
+  static constexpr int CT = CTV;
   static constexpr int THREADS = CT * T;
   // lanes of a warp are different COLUMNS at the same offset: skew each column's buffer by one cf32 so
   // they fall into different banks (SMEM_ELEMS is a multiple of 16 cf32 = one 128-byte bank row)
@@ -207,12 +208,12 @@ struct ColLaunch {
   static constexpr size_t SMEM = (size_t)CT * CSTRIDE * sizeof(float2);
 };
 
-template <int N1, bool INV, bool FIRST>
-__global__ void __launch_bounds__(ColLaunch<N1>::THREADS, 1024 / ColLaunch<N1>::THREADS)
+template <int N1, bool INV, bool FIRST, int CTV = col_default_ct(N1)>
+__global__ void __launch_bounds__(ColLaunch<N1, CTV>::THREADS, 1024 / ColLaunch<N1, CTV>::THREADS)
 fft_col_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float2* __restrict__ tw, const float2* __restrict__ wlo,
                const float2* __restrict__ whi, size_t stride, size_t frame_elems, float scale, int do_scale) {
   using C = FftCfg<N1>;
-  using LC = ColLaunch<N1>;
+  using LC = ColLaunch<N1, CTV>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* smem = reinterpret_cast<float2*>(smem_raw);
   const int c = threadIdx.x % LC::CT;
@@ -258,10 +259,10 @@ fft_col_kernel(const float2* __restrict__ in, float2* __restrict__ out, const fl
   }
 }
 
-template <int N1, bool FIRST>
+template <int N1, bool FIRST, int CTV = col_default_ct(N1)>
 static void launch_col_n(const float2* in, float2* out, const float2* tw, const float2* wlo, const float2* whi, size_t ncols,
                          size_t frames, size_t frame_elems, bool inverse, bool do_scale, float scale, cudaStream_t st) {
-  using LC = ColLaunch<N1>;
+  using LC = ColLaunch<N1, CTV>;
   auto launch = [&](auto kern) {
     (void)resident_ctas((const void*)kern, LC::THREADS, LC::SMEM);   // shared-memory opt-in, once per device
     for (size_t f0 = 0; f0 < frames; f0 += 32768) {
@@ -271,8 +272,8 @@ static void launch_col_n(const float2* in, float2* out, const float2* tw, const 
                                                do_scale);
     }
   };
-  if (inverse) launch(fft_col_kernel<N1, true, FIRST>);
-  else launch(fft_col_kernel<N1, false, FIRST>);
+  if (inverse) launch(fft_col_kernel<N1, true, FIRST, CTV>);
+  else launch(fft_col_kernel<N1, false, FIRST, CTV>);
 }
 
 bool fft_big_supported(size_t n) { return n > 16384 && n <= ((size_t)1 << 24) && (n & (n - 1)) == 0; }
