@@ -55,6 +55,7 @@ for rep in range(1):
         fr = n // nn
         ae.Cfft.with_len(nn).ifwd(dx.view(0, fr * nn), ae.Scale.SN, howmany=fr)
     ae.Cfft.with_len(1 << 16).ifwd(dx, ae.Scale.SN, howmany=n >> 16)      # four-step
+    ae.Cfft.with_len(1 << 20).ifwd(dx, ae.Scale.SN, howmany=n >> 20)      # four-step, 1024 x 1024
     from aether_primitives_b200.chain import FftFirDemod
     cb = ae.DeviceBits.with_capacity(2 * n)
     FftFirDemod(1024, make_taps(64), ae.Scale.SN).run(dx, cb)              # headline chain
