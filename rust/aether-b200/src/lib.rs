@@ -468,9 +468,12 @@ pub mod pipeline {
         // user: the stage; item: a heap cell holding the travelling value
         let stage = unsafe { &*(user as *const RefCell<Stage>) };
         let cell = unsafe { &mut *(item as *mut Option<Boxed>) };
-        let v = cell.take().expect("pipeline item");
-        *cell = Some((stage.borrow_mut().op)(v));
-        sys::AE_OK
+        // a panic must not unwind through the C frames of ae_pipeline_send: report it as a failed stage
+        let r = std::panic::catch_unwind(std::panic::AssertUnwindSafe(|| {
+            let v = cell.take().expect("pipeline item");
+            *cell = Some((stage.borrow_mut().op)(v));
+        }));
+        if r.is_ok() { sys::AE_OK } else { sys::AE_EARG }
     }
 
     pub struct Pipeline<I, O> { st: Rc<RefCell<State>>, _m: std::marker::PhantomData<(I, O)> }
@@ -507,7 +510,9 @@ pub mod pipeline {
         pub fn send(&self, item: I) {
             let cell: *mut Option<Boxed> = Box::into_raw(Box::new(Some(Box::new(item) as Boxed)));
             let h = self.st.borrow().h;
-            unsafe { ck(sys::ae_pipeline_send(h, cell as *mut c_void)) }
+            let st = unsafe { sys::ae_pipeline_send(h, cell as *mut c_void) };
+            if st != sys::AE_OK { drop(unsafe { Box::from_raw(cell) }); }      // a failed stage: the item is not in flight
+            ck(st)
         }
     }
     impl<O: 'static> Receiver<O> {
