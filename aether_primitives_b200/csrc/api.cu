@@ -1802,6 +1802,11 @@ extern "C" {
 ae_status ae_graph_begin(void) {
   Ctx* c;
   TRY(get_ctx(&c));
+  // VecOps recorded before the bracket run now, once - not as part of every replay
+  {
+    std::vector<ae_vec*> snap = c->pending;
+    for (ae_vec* v : snap) TRY(flush_vec(v));
+  }
   CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
   return AE_OK;
 }
@@ -1809,8 +1814,16 @@ ae_status ae_graph_end(ae_graph** out) {
   if (!out) return fail(AE_EARG, "null");
   Ctx* c;
   TRY(get_ctx(&c));
+  // VecOps recorded inside the bracket and not yet run belong to the graph
+  ae_status fst = AE_OK;
+  {
+    std::vector<ae_vec*> snap = c->pending;
+    for (ae_vec* v : snap)
+      if (fst == AE_OK) fst = flush_vec(v);
+  }
   cudaGraph_t g = nullptr;
-  CK(cudaStreamEndCapture(c->stream, &g));
+  CK(cudaStreamEndCapture(c->stream, &g));       // always leave capture mode
+  if (fst != AE_OK) { if (g) cudaGraphDestroy(g); return fst; }
   cudaGraphExec_t ex = nullptr;
   const cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
   if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(AE_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }

@@ -302,7 +302,8 @@ ae_status ae_bits_download_async(ae_bits* b, uint8_t* host, size_t n);
  * capture apply: size every output beforehand (nothing may reallocate) and call nothing that synchronises
  * (downloads, ae_sync, ae_stats_read) inside the bracket.  Host-side state advances at record time: an Awgn stream
  * offset is baked into each recorded launch, so the k launches of one recording use k consecutive noise blocks and
- * every replay repeats them. */
+ * every replay repeats them.  VecOps still pending when the bracket opens run once, before it; VecOps recorded inside it
+ * and not yet run when it closes are part of the graph. */
 typedef struct ae_graph ae_graph;
 ae_status ae_graph_begin(void);
 ae_status ae_graph_end(ae_graph** out);

@@ -171,3 +171,13 @@ def test_cuda_graph_records_then_replays(ae):
     assert np.array_equal(got.to_numpy(), want.to_numpy())
     g.close()
     g2.close()
+    # VecOps recorded BEFORE the bracket run once, now; VecOps recorded INSIDE and never flushed still belong to the graph
+    b = ae.DeviceVec.from_numpy(x)
+    b.vec_scale(3.0)                                    # pending when the bracket opens
+    with ae.Graph() as g3:
+        b.vec_scale(2.0)                                # pending when the bracket closes
+    assert np.array_equal(b.to_numpy(), x * 3)
+    g3.launch()
+    g3.launch()
+    assert np.array_equal(b.to_numpy(), x * 12)
+    g3.close()
