@@ -979,6 +979,7 @@ struct ae_fir {
   float2* d_H;
   float2* d_tw;
   float2* d_x2tw;  // K4b (1024-point blocks): per-thread twiddle rows of the packed transform, else null
+  std::vector<float2> h_taps;   // host copy, tp entries: the direct kernel takes short filters as kernel parameters
 };
 
 extern "C" {
@@ -1010,6 +1011,7 @@ ae_status ae_fir_create(const ae_cf32* taps_host, size_t ntaps, int mode, ae_fir
     void* p;
     std::vector<float2> h(f->tp, make_float2(0.f, 0.f));
     for (size_t i = 0; i < ntaps; ++i) h[i] = make_float2(taps_host[i].re, taps_host[i].im);
+    f->h_taps = h;
     TRY(dev_alloc(c, f->tp * sizeof(float2), &p)); f->d_taps = (float2*)p;
     CK(cudaMemcpyAsync(f->d_taps, h.data(), f->tp * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
     TRY(dev_alloc(c, f->tp * sizeof(float2), &p)); f->d_hist = (float2*)p;
@@ -1084,7 +1086,7 @@ ae_status ae_fir_exec(ae_fir* f, ae_vec* in, ae_vec* out, size_t frame_len) {
     mode = AE_FIR_OVERLAP_SAVE;
   }
   const float2* hist = frame_len ? nullptr : f->d_hist;
-  if (mode == AE_FIR_DIRECT) launch_fir_direct(x, y, n, f->d_taps, f->tp, hist, frame_len, c->sm_count, c->stream);
+  if (mode == AE_FIR_DIRECT) launch_fir_direct(x, y, n, f->d_taps, f->tp, hist, frame_len, c->sm_count, c->stream, f->h_taps.data());
   else if (f->d_x2tw) launch_fir_os_x2(x, y, n, f->d_H, f->d_x2tw, f->ntaps, hist, frame_len, c->stream);
   else launch_fir_overlap_save(x, y, n, f->d_H, f->d_tw, f->nfft, f->ntaps, hist, frame_len, c->stream);
   CKL(1);

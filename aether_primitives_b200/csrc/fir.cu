@@ -5,6 +5,8 @@
 // a carried history of T-1 samples (streaming) or zero state at the start of every frame.
 // Parity tier T1: EVM against the f64 direct form (tests/test_gpu_fir.py).
 #include <cstdlib>
+#include <cstring>
+#include <type_traits>
 
 #include "chain_x2.cuh"
 #include "fft_device.cuh"
@@ -99,17 +101,26 @@ __device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsig
   return d;
 }
 
+// CTAPS: the tap pairs come from the kernel parameters (constant bank -> uniform registers: `FFMA2 R, R, UR, R`), so a
+// packed FMA reads two vector-register pairs instead of three.  Measured at 64 taps: the three-register form is bound by
+// register-file bandwidth at 74 Gsamples/s (57 % of what the FMA pipe allows), whatever the rest of the loop does.
+constexpr int kFirCTaps = 128;
+struct FirTapsC { ulonglong2 h[kFirCTaps]; };                 // (hr, hr), (-hi, hi) per tap; 2 KB of parameters
+
+template <bool CTAPS>
 __global__ void __launch_bounds__(kFirThreads)
 fir_direct_x2_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_t n, const float2* __restrict__ taps, int tp,
-                     const float2* __restrict__ history, size_t frame_len) {
+                     const float2* __restrict__ history, size_t frame_len, const __grid_constant__ FirTapsC tc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* hs = reinterpret_cast<float4*>(smem_raw);          // tp entries (hr, hr, -hi, hi)
-  float2* xs = reinterpret_cast<float2*>(hs + tp);            // padded tile: kFirTile + tp inputs
+  float4* hs = reinterpret_cast<float4*>(smem_raw);          // tp entries (hr, hr, -hi, hi); unused with CTAPS
+  float2* xs = reinterpret_cast<float2*>(hs + (CTAPS ? 0 : tp));   // padded tile: kFirTile + tp inputs
   const long long tile0 = (long long)blockIdx.x * kFirTile;
   const int n_in = kFirTile + tp;
-  for (int i = threadIdx.x; i < tp; i += kFirThreads) {
-    const float2 h = __ldg(taps + i);
-    hs[i] = make_float4(h.x, h.x, -h.y, h.y);
+  if (!CTAPS) {
+    for (int i = threadIdx.x; i < tp; i += kFirThreads) {
+      const float2 h = __ldg(taps + i);
+      hs[i] = make_float4(h.x, h.x, -h.y, h.y);
+    }
   }
   for (int i = threadIdx.x; i < n_in; i += kFirThreads) {
     const long long g = tile0 - tp + i;
@@ -135,25 +146,33 @@ fir_direct_x2_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_
     w[s] = f2_pack(v.x, v.y);
     wsw[s] = f2_pack(v.y, v.x);
   }
-  for (int kb = 0; kb < tp; kb += kFirS) {
+  // tp and base are multiples of 8, so the eight samples a block of eight taps pulls in, x[n0 - kb - 1 .. n0 - kb - 8], sit in
+  // ONE padded group of the tile: one pointer per block, compile-time offsets inside it.  Threads whose window never
+  // reaches back before their frame (all of them when streaming) skip the per-tap zeroing test.
+  const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(hs);      // (hr, hr), (-hi, hi): one 128-bit broadcast read per tap
+  auto taps_loop = [&](auto check_tag) {
+    constexpr bool CHECK = decltype(check_tag)::value;
+    for (int kb = 0; kb < tp; kb += kFirS) {
+      const float2* xp = xs + fir_pad(base - kb - kFirS);
 #pragma unroll
-    for (int kk = 0; kk < kFirS; ++kk) {
-      const float4 h = hs[kb + kk];
-      const unsigned long long ha = f2_pack(h.x, h.y), hb = f2_pack(h.z, h.w);
+      for (int kk = 0; kk < kFirS; ++kk) {
+        const ulonglong2 h = CTAPS ? tc.h[kb + kk] : hp[kb + kk];
 #pragma unroll
-      for (int s = 0; s < kFirS; ++s) {
-        const int j = (s - kk) & (kFirS - 1);
-        acc[s] = f2_fma(w[j], ha, acc[s]);
-        acc[s] = f2_fma(wsw[j], hb, acc[s]);
+        for (int s = 0; s < kFirS; ++s) {
+          const int j = (s - kk) & (kFirS - 1);
+          acc[s] = f2_fma(w[j], h.x, acc[s]);
+          acc[s] = f2_fma(wsw[j], h.y, acc[s]);
+        }
+        float2 v = xp[kFirS - 1 - kk];                     // x[n0 - (kb + kk + 1)]
+        if (CHECK && kb + kk + 1 > kz) v = make_float2(0.0f, 0.0f);
+        const int jn = (kFirS - 1 - kk) & (kFirS - 1);
+        w[jn] = f2_pack(v.x, v.y);
+        wsw[jn] = f2_pack(v.y, v.x);
       }
-      const int k1 = kb + kk + 1;
-      float2 v = xs[fir_pad(base - k1)];
-      if (k1 > kz) v = make_float2(0.0f, 0.0f);
-      const int jn = (kFirS - 1 - kk) & (kFirS - 1);
-      w[jn] = f2_pack(v.x, v.y);
-      wsw[jn] = f2_pack(v.y, v.x);
     }
-  }
+  };
+  if (kz == 0x7fffffff) taps_loop(std::false_type{});
+  else taps_loop(std::true_type{});
   if ((size_t)(n0 + kFirS) <= n && ((uintptr_t)(y + n0) % 16) == 0) {
     ulonglong2* o = reinterpret_cast<ulonglong2*>(y + n0);
 #pragma unroll
@@ -166,14 +185,31 @@ fir_direct_x2_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_
 }
 
 void launch_fir_direct(const float2* x, float2* y, size_t n, const float2* taps_padded, int tp, const float2* history,
-                       size_t frame_len, int, cudaStream_t st) {
+                       size_t frame_len, int, cudaStream_t st, const float2* taps_host_padded) {
   if (n == 0) return;
   static const char* scalar = getenv("AE_FIR_SCALAR");
+  static const char* no_ctaps = getenv("AE_FIR_NO_CTAPS");
   if (!scalar) {
     const size_t n_in2 = (size_t)kFirTile + tp;
-    const size_t smem2 = (size_t)tp * sizeof(float4) + (n_in2 + n_in2 / 8 + 2) * sizeof(float2);
-    if (smem2 > 48 * 1024) cudaFuncSetAttribute(fir_direct_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    fir_direct_x2_kernel<<<(unsigned)((n + kFirTile - 1) / kFirTile), kFirThreads, smem2, st>>>(x, y, n, taps_padded, tp, history, frame_len);
+    const bool ctaps = taps_host_padded && tp <= kFirCTaps && !no_ctaps;
+    const size_t smem2 = (ctaps ? 0 : (size_t)tp * sizeof(float4)) + (n_in2 + n_in2 / 8 + 2) * sizeof(float2);
+    const unsigned grid = (unsigned)((n + kFirTile - 1) / kFirTile);
+    FirTapsC tc;
+    if (ctaps) {
+      for (int i = 0; i < kFirCTaps; ++i) {
+        const float2 h = i < tp ? taps_host_padded[i] : make_float2(0.0f, 0.0f);
+        const float nh = -h.y;
+        unsigned hr, hi, nhi;
+        memcpy(&hr, &h.x, 4); memcpy(&hi, &h.y, 4); memcpy(&nhi, &nh, 4);
+        tc.h[i].x = ((unsigned long long)hr << 32) | hr;       // (hr, hr)
+        tc.h[i].y = ((unsigned long long)hi << 32) | nhi;      // (-hi, hi)
+      }
+      fir_direct_x2_kernel<true><<<grid, kFirThreads, smem2, st>>>(x, y, n, taps_padded, tp, history, frame_len, tc);
+      return;
+    }
+    memset(&tc, 0, sizeof(tc));
+    if (smem2 > 48 * 1024) cudaFuncSetAttribute(fir_direct_x2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    fir_direct_x2_kernel<false><<<grid, kFirThreads, smem2, st>>>(x, y, n, taps_padded, tp, history, frame_len, tc);
     return;
   }
   const size_t n_in = (size_t)kFirTile + tp;

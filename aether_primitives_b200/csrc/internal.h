@@ -90,7 +90,7 @@ void launch_fft_generic(const float2* in, float2* out, float2* scratch, size_t n
 // ---- K3/K4 FIR -------------------------------------------------------------------------------
 void launch_fir_direct(const float2* x, float2* y, size_t n, const float2* taps_padded, int ntaps_padded,
                        const float2* history /*ntaps_padded-1 samples or null*/, size_t frame_len, int sm_count,
-                       cudaStream_t st);
+                       cudaStream_t st, const float2* taps_host_padded = nullptr /* host copy: short filters keep their taps in the constant bank */);
 bool fir_os_supported(size_t nfft);
 // H = FFT_nfft(taps)/nfft (exp(-) convention); L = nfft - ntaps + 1 outputs per segment
 void launch_fir_overlap_save(const float2* x, float2* y, size_t n, const float2* H, const float2* tw, size_t nfft,
