@@ -104,13 +104,14 @@ __device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsig
 // CTAPS: the tap pairs come from the kernel parameters (constant bank -> uniform registers: `FFMA2 R, R, UR, R`), so a
 // packed FMA reads two vector-register pairs instead of three.  Measured at 64 taps: the three-register form is bound by
 // register-file bandwidth at 74 Gsamples/s (57 % of what the FMA pipe allows), whatever the rest of the loop does.
-constexpr int kFirCTaps = 128;
-struct FirTapsC { ulonglong2 h[kFirCTaps]; };                 // (hr, hr), (-hi, hi) per tap; 2 KB of parameters
+template <int NT>
+struct FirTapsC { ulonglong2 h[NT]; };                        // (hr, hr), (-hi, hi) per tap: 2 KB (128 taps) or 16 KB (1024) of parameters
+constexpr int kFirCTapsSmall = 128, kFirCTapsLarge = 1024;
 
-template <bool CTAPS>
+template <bool CTAPS, int NT>
 __global__ void __launch_bounds__(kFirThreads)
 fir_direct_x2_kernel(const float2* __restrict__ x, float2* __restrict__ y, size_t n, const float2* __restrict__ taps, int tp,
-                     const float2* __restrict__ history, size_t frame_len, const __grid_constant__ FirTapsC tc) {
+                     const float2* __restrict__ history, size_t frame_len, const __grid_constant__ FirTapsC<NT> tc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* hs = reinterpret_cast<float4*>(smem_raw);          // tp entries (hr, hr, -hi, hi); unused with CTAPS
   float2* xs = reinterpret_cast<float2*>(hs + (CTAPS ? 0 : tp));   // padded tile: kFirTile + tp inputs
@@ -191,25 +192,37 @@ void launch_fir_direct(const float2* x, float2* y, size_t n, const float2* taps_
   static const char* no_ctaps = getenv("AE_FIR_NO_CTAPS");
   if (!scalar) {
     const size_t n_in2 = (size_t)kFirTile + tp;
-    const bool ctaps = taps_host_padded && tp <= kFirCTaps && !no_ctaps;
+    const bool ctaps = taps_host_padded && tp <= kFirCTapsLarge && !no_ctaps;
     const size_t smem2 = (ctaps ? 0 : (size_t)tp * sizeof(float4)) + (n_in2 + n_in2 / 8 + 2) * sizeof(float2);
     const unsigned grid = (unsigned)((n + kFirTile - 1) / kFirTile);
-    FirTapsC tc;
-    if (ctaps) {
-      for (int i = 0; i < kFirCTaps; ++i) {
+    auto fill = [&](ulonglong2* dst, int nt) {
+      for (int i = 0; i < nt; ++i) {
         const float2 h = i < tp ? taps_host_padded[i] : make_float2(0.0f, 0.0f);
         const float nh = -h.y;
         unsigned hr, hi, nhi;
         memcpy(&hr, &h.x, 4); memcpy(&hi, &h.y, 4); memcpy(&nhi, &nh, 4);
-        tc.h[i].x = ((unsigned long long)hr << 32) | hr;       // (hr, hr)
-        tc.h[i].y = ((unsigned long long)hi << 32) | nhi;      // (-hi, hi)
+        dst[i].x = ((unsigned long long)hr << 32) | hr;        // (hr, hr)
+        dst[i].y = ((unsigned long long)hi << 32) | nhi;       // (-hi, hi)
       }
-      fir_direct_x2_kernel<true><<<grid, kFirThreads, smem2, st>>>(x, y, n, taps_padded, tp, history, frame_len, tc);
+    };
+    if (ctaps && tp <= kFirCTapsSmall) {
+      FirTapsC<kFirCTapsSmall> tc;
+      fill(tc.h, kFirCTapsSmall);
+      fir_direct_x2_kernel<true, kFirCTapsSmall><<<grid, kFirThreads, smem2, st>>>(x, y, n, taps_padded, tp, history, frame_len, tc);
       return;
     }
-    memset(&tc, 0, sizeof(tc));
-    if (smem2 > 48 * 1024) cudaFuncSetAttribute(fir_direct_x2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    fir_direct_x2_kernel<false><<<grid, kFirThreads, smem2, st>>>(x, y, n, taps_padded, tp, history, frame_len, tc);
+    if (ctaps) {
+      FirTapsC<kFirCTapsLarge> tc;
+      fill(tc.h, kFirCTapsLarge);
+      if (smem2 > 48 * 1024)
+        cudaFuncSetAttribute(fir_direct_x2_kernel<true, kFirCTapsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+      fir_direct_x2_kernel<true, kFirCTapsLarge><<<grid, kFirThreads, smem2, st>>>(x, y, n, taps_padded, tp, history, frame_len, tc);
+      return;
+    }
+    FirTapsC<1> none;
+    memset(&none, 0, sizeof(none));
+    if (smem2 > 48 * 1024) cudaFuncSetAttribute(fir_direct_x2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    fir_direct_x2_kernel<false, 1><<<grid, kFirThreads, smem2, st>>>(x, y, n, taps_padded, tp, history, frame_len, none);
     return;
   }
   const size_t n_in = (size_t)kFirTile + tp;

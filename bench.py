@@ -265,6 +265,16 @@ def extras(torch, ae, d_in, frames, hbm_peak, steps=5, warmup=3, rank=0, world=1
                        ("fir1024_overlap_save", F.Fir(make_taps(1024), F.OVERLAP_SAVE))):
         t = timed(torch, lambda: filt.filter(a, b), steps, warmup) / steps
         rec(name, 16.0 * m, t, m, "samples")
+    out["fir64_direct"]["fp32_TFLOP/s"] = 8.0 * 64 * m / (out["fir64_direct"]["ms"] * 1e-3) / 1e12
+    # config 3 also names the 1024-tap direct form: 8192 flop per sample, FP32-bound by construction; a 2^24-sample slice
+    md = min(m, 1 << 24)
+    fd = F.Fir(make_taps(1024), F.DIRECT)
+    ad, bd = a.view(0, md), b.view(0, md)
+    t = timed(torch, lambda: fd.filter(ad, bd), 2, 1) / 2
+    rec("fir1024_direct", 16.0 * md, t, md, "samples")
+    out["fir1024_direct"]["fp32_TFLOP/s"] = 8.0 * 1024 * md / t / 1e12
+    out["fir1024_direct"]["bytes_note"] = "FP32-bound by construction (74 TFLOP/s peak = 9 Gsamples/s); 2^24-sample slice"
+    del fd, ad, bd
     # config 3 across GPUs: ONE stream of 2^28 samples, rank r filters [r n/R - halo, (r+1) n/R) and keeps its n/R outputs
     # (strong scaling; "units" are this rank's outputs, so the combined line is the rate of the whole stream)
     total = 1 << 28
