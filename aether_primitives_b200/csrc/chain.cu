@@ -372,21 +372,31 @@ ofdm_chain_kernel(size_t frames, uint64_t first_frame, float noise_scale, int tw
     frame_sync<C::T>(f);
     fft_frame<N, FWD_INV>(v, sm, tw, t, f);
     float e_pow = 0.0f;
-    unsigned risky = 0, rxb = 0;
+    unsigned rxb = 0;
+    // the sign test is the reference's decision when min |component| > 2^-21 (1 + max |component|)^2 (common.cuh); the bound
+    // grows with the maximum, so ONE test per thread on the minimum and the NaN-propagating maximum of its 32 components
+    // replaces sixteen per-symbol tests (FMNMX3: two new values per instruction)
+    float mx = 0.0f, mn = 3.0e38f;
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
       v[m] = cx_scale_exact(v[m], sn);
       const unsigned two = (txb >> (2 * m)) & 3u;
-      if (!qpsk_fast_ok(v[m])) risky |= 1u << m;
+      asm("max.NaN.f32 %0, %0, %1, %2;" : "+f"(mx) : "f"(fabsf(v[m].x)), "f"(fabsf(v[m].y)));
+      asm("min.f32 %0, %0, %1, %2;" : "+f"(mn) : "f"(fabsf(v[m].x)), "f"(fabsf(v[m].y)));
       rxb |= ((__float_as_uint(v[m].x) >> 31) | ((__float_as_uint(v[m].y) >> 31) << 1)) << (2 * m);
       const float2 ref = qpsk_symbol(two);
       const float dr = v[m].x - ref.x, di = v[m].y - ref.y;
       e_pow += dr * dr + di * di;
     }
-    if (risky) {
+    const float uu = fmaf(mx, 6.9053396600248786e-4f, 6.9053396600248786e-4f);   // 2^-10.5 (1 + max)
+    if (!(mn > uu * uu)) {             // rare: a component near an axis, NaN or inf somewhere in this thread's symbols
+#pragma unroll 1
+      for (int m = 0; m < 16; ++m) {
+        float2 sv = v[0];
 #pragma unroll
-      for (int m = 0; m < 16; ++m)
-        if (risky & (1u << m)) rxb = (rxb & ~(3u << (2 * m))) | (demod_qpsk_exact_slow(v[m]) << (2 * m));
+        for (int k = 1; k < 16; ++k) sv = (m == k) ? v[k] : sv;       // select without dynamic register indexing
+        if (!qpsk_fast_ok(sv)) rxb = (rxb & ~(3u << (2 * m))) | (demod_qpsk_exact_slow(sv) << (2 * m));
+      }
     }
     errs += __popc(rxb ^ txb);
     e_sum += (double)e_pow;
