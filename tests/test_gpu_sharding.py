@@ -57,6 +57,35 @@ def test_sharded_fir_equals_unsharded_bit_for_bit(ae, mode, t, world):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "sharded FIR differs from the unsharded stream"
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_sharded_fir_random_shapes(ae, seed):
+    """random stream lengths (shorter than a block, not a multiple of the hop, shards smaller than the halo), tap counts,
+    shard counts and both modes: the concatenation of the shards is the unsharded stream, bit for bit"""
+    from aether_primitives_b200 import fir as F
+    from aether_primitives_b200.sharding import ShardedFir
+
+    rng = np.random.default_rng(1000 + seed)
+    t = int(rng.choice([1, 2, 17, 64, 65, 200, 256, 1024]))
+    world = int(rng.integers(1, 10))
+    n = int(rng.choice([rng.integers(1, 900), rng.integers(900, 5000), rng.integers(5000, 200_000)]))
+    m = F.DIRECT if seed % 2 else F.OVERLAP_SAVE
+    x, h = rnd(n, seed), (taps(t) if t > 2 else rnd(t, 9))
+    whole = ae.DeviceVec.zeros(n)
+    F.Fir(h, m).filter(ae.DeviceVec.from_numpy(x), whole)
+    want = whole.to_numpy()
+    got = []
+    for r in range(world):
+        sh = ShardedFir(h, n, r, world, m)
+        lo_in, hi = sh.input_range()
+        assert 0 <= lo_in <= sh.lo <= sh.hi <= hi <= n
+        if sh.hi == sh.lo:
+            continue                                   # more ranks than samples: this one owns nothing
+        got.append(sh.filter(ae.DeviceVec.from_numpy(x[lo_in:hi])).to_numpy())
+    got = np.concatenate(got)
+    assert got.size == n
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "t=%d world=%d n=%d mode=%d" % (t, world, n, m)
+
+
 def test_sharded_fir_rejects_wrong_input_length(ae):
     from aether_primitives_b200.sharding import ShardedFir
 
