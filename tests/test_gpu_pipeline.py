@@ -112,3 +112,29 @@ def test_stage_error_and_empty_recv(ae):
         if rx.in_flight() == 2:
             assert rx.recv() == 2 * (i - 1 + 1)
     assert rx.recv() == 10
+
+
+@pytest.mark.parametrize("depth", [1, 2, 5])
+def test_many_stages_and_depths(ae, depth):
+    """five VecOps stages on five streams; every depth, more items than slots: each item sees every stage exactly once, in order"""
+    n, items = 4096, 11
+    xs = [rnd(n, 300 + i) for i in range(items)]
+    p = ae.pipeline.Pipeline.new("s0", lambda v: v.vec_scale(2.0), depth=depth)
+    for k in range(1, 5):
+        p = p.add_stage("s%d" % k, (lambda kk: (lambda v: v.vec_scale(float(kk + 2))))(k))
+    tx, rx = p.finish()
+    out = []
+    for x in xs:
+        if rx.in_flight() == depth:
+            out.append(rx.recv().to_numpy())
+        tx.send(ae.DeviceVec.from_numpy(x))
+    while rx.in_flight():
+        out.append(rx.recv().to_numpy())
+    assert len(out) == items
+    for x, y in zip(xs, out):
+        want = x.copy()
+        for f in (2.0, 3.0, 4.0, 5.0, 6.0):
+            want = (want * np.float32(f)).astype(np.complex64)
+        assert np.array_equal(y, want)
+    rep = rx.report()
+    assert len(rep) == 5 and all(r["processed"] == items for r in rep)
