@@ -13,8 +13,12 @@
  *    non-zero status to the reference's panic message.  ae_last_error_string() gives it.
  *  - cf32 = two f32 back to back (src/lib.rs:8-12); bits are one u8 per bit
  *    (src/modulation.rs:102-103).
- *  - handles are Send, not Sync: one caller at a time.  All work of a process is issued
- *    on one CUDA stream per device (ae_set_stream), so calls are ordered as issued.
+ *  - threading: the per-device context (pending op tapes, table caches, the current stream) is not
+ *    locked.  All calls that touch one device, whatever the handle, must come from one thread
+ *    at a time; different devices may be driven from different threads.  Error strings and the
+ *    current device (ae_init) are per thread.  All work of a device is issued on one CUDA
+ *    stream (ae_set_stream), so calls are ordered as issued; stage pipelines (ae_pipeline_*) get
+ *    their concurrency from CUDA streams, not from host threads.
  *  - VecOps calls on an ae_vec are RECORDED on the handle's op tape and executed as ONE
  *    fused elementwise kernel when a consumer needs the data (ae_vec_flush, download, FFT,
  *    FIR, use as operand, free).  Results are visible after ae_sync()/download.
